@@ -1,0 +1,916 @@
+// hpf_engine.cu -- host side of libhpf_b200.so: the hpf_ctx object and the C ABI
+// declared in include/hpf_cuda.h.  Everything numerical runs in the kernels of
+// hpf_kernels.cuh on the ctx's own stream; there is no CPU compute path.
+//
+// HBM layout per parameter side (theta: R = local users, beta: R = items), all
+// fp32, row stride Kp = K rounded up to 4 floats (16-byte rows for 128-bit loads):
+//   A      [R x Kp]  exp(Elog - rowmax)      sweep input (gathered by the other side)
+//   Elog   [R x Kp]  expected log            fallback path + hpf_get_state
+//   Ev     [R x Kp]  expectation             rate sums, held-out ll, top-N
+//   shape  [R x Kp]  Gamma shape             hpf_get_state / checkpoints
+//   rate   [R x Kp] (hier) or [Kp]           hpf_get_state / checkpoints
+//   T      [R x Kp]  sweep output sum (y/Z) * A_other   (+ Tpart for split rows)
+//   Tdirect[R x Kp]  exact-fallback accumulator (all zero in normal operation)
+// plus per-row vectors (shift, xi/eta GPArray, bias GPMatrix, aux) and the
+// ratings in both orientations (CSR for the user pass, CSC for the item pass).
+#include "../../include/hpf_cuda.h"
+#include "hpf_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace hpf;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+// ---- NCCL through dlopen: single-GPU users never need the library ----------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7 };
+enum { ncclSum = 0 };
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err)
+  {
+    if (handle) return true;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks expected symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+struct WorkList {       // segments of one orientation, sorted by descending length
+  uint4 *seg = nullptr;
+  uint32_t *seg_out = nullptr;
+  uint32_t nsegs = 0, npartial = 0, nmulti = 0;
+  uint32_t *multi_row = nullptr, *multi_first = nullptr, *multi_cnt = nullptr;
+  const uint32_t *idx = nullptr; // device, per nonzero
+  const uint8_t *y = nullptr;
+};
+
+struct Side {
+  uint32_t R = 0;
+  float *A = nullptr, *Elog = nullptr, *Ev = nullptr, *shape = nullptr, *rate = nullptr;
+  float *T = nullptr, *Tpart = nullptr, *Tdirect = nullptr, *shift = nullptr;
+  float *pr_shape = nullptr, *pr_rate = nullptr, *pr_Ev = nullptr;           // GPArray (hier)
+  float *b_shape = nullptr, *b_rate = nullptr, *b_Ev = nullptr, *b_Elog = nullptr; // bias GPMatrix
+  float *Tb = nullptr, *Tbpart = nullptr, *Tbdirect = nullptr;
+  float2 *aux = nullptr;
+  float *colsum = nullptr;         // [Kp] sum over rows of Ev (this side)
+  float *colsum_partial = nullptr; // [update_grid x Kp]
+  uint32_t *direct_flag = nullptr;
+  uint32_t update_grid = 0;
+  size_t part_rows_cap = 0;
+  WorkList wl;
+  double prior_shape = 0.3, prior_rate = 0.3, pr_prior_shape = 0.3, pr_prior_rate = 0.3;
+  double bias_prior_shape = 0.3, bias_prior_rate = 0.3;
+  bool have_state = false, have_pr = false, have_bias = false;
+};
+
+} // namespace
+
+struct hpf_ctx {
+  hpf_config cfg;
+  uint32_t K = 0, Kp = 0, K4 = 0;
+  bool hier = false, bias = false, binary = false, jacobi = false;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  bool profiling = false;
+  std::string err;
+  std::vector<void *> allocs;
+  uint64_t device_bytes = 0;
+  Side th, be; // theta (users), beta (items)
+  // ratings
+  uint64_t nnz = 0;
+  uint32_t *csr_idx = nullptr, *csc_idx = nullptr;
+  uint8_t *csr_y = nullptr, *csc_y = nullptr;
+  uint32_t seg_len = 256;
+  int sweep_g = 0, sweep_v = 0;
+  bool aux_dirty = true, ratings_set = false, th_colsum_global = false;
+  // item-side reduce block [T_beta | Tb_beta | colsum_theta] (one allreduce)
+  float *redblock = nullptr;
+  size_t red_count = 0;
+  float *colsum_theta_old = nullptr; // -novb
+  unsigned long long *slow_count = nullptr;
+  double *logfact = nullptr, *ll_blocks = nullptr, *ll_out = nullptr;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // stats
+  uint64_t launches = 0, iterations = 0;
+  float last_ms = 0.f;
+};
+
+namespace {
+
+int fail(hpf_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(c, e_ == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                               \
+  } while (0)
+
+template <class T> int dalloc(hpf_ctx *c, T **p, size_t count, bool zero = true)
+{
+  *p = nullptr;
+  if (count == 0) count = 1;
+  void *q = nullptr;
+  CU(cudaMalloc(&q, count * sizeof(T)));
+  c->allocs.push_back(q);
+  c->device_bytes += count * sizeof(T);
+  if (zero) CU(cudaMemsetAsync(q, 0, count * sizeof(T), c->stream));
+  *p = (T *)q;
+  return 0;
+}
+
+int dfree(hpf_ctx *c, void *p)
+{
+  if (!p) return 0;
+  auto it = std::find(c->allocs.begin(), c->allocs.end(), p);
+  if (it != c->allocs.end()) c->allocs.erase(it);
+  cudaFree(p);
+  return 0;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+uint32_t row_grid(const hpf_ctx *c, uint32_t R)
+{
+  uint32_t need = (R + kUpdateWarps - 1) / kUpdateWarps;
+  uint32_t cap = (uint32_t)c->sm_count * 8u;
+  return std::max(1u, std::min(need, cap));
+}
+
+// pick lanes-per-nonzero G and float4-per-lane V: smallest G with V <= 7
+void pick_sweep_shape(hpf_ctx *c)
+{
+  int g = 1;
+  while (g < 32 && (int)((c->K4 + g - 1) / g) > 7) g *= 2;
+  if (const char *e = getenv("HPF_SWEEP_G")) {
+    int eg = atoi(e);
+    if (eg == 1 || eg == 2 || eg == 4 || eg == 8 || eg == 16 || eg == 32)
+      if ((c->K4 + eg - 1) / eg <= 8) g = eg;
+  }
+  c->sweep_g = g;
+  c->sweep_v = (int)((c->K4 + g - 1) / g);
+}
+
+int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
+{
+  s.R = R;
+  const size_t rk = (size_t)R * c->Kp;
+  TRY(dalloc(c, &s.A, rk));
+  TRY(dalloc(c, &s.Elog, rk));
+  TRY(dalloc(c, &s.Ev, rk));
+  TRY(dalloc(c, &s.shape, rk));
+  TRY(dalloc(c, &s.rate, c->hier ? rk : (size_t)c->Kp));
+  TRY(dalloc(c, &s.Tdirect, rk));
+  TRY(dalloc(c, &s.shift, R));
+  TRY(dalloc(c, &s.direct_flag, 1));
+  if (c->hier) {
+    TRY(dalloc(c, &s.pr_shape, R));
+    TRY(dalloc(c, &s.pr_rate, R));
+    TRY(dalloc(c, &s.pr_Ev, R));
+  }
+  if (c->bias) {
+    TRY(dalloc(c, &s.b_shape, R));
+    TRY(dalloc(c, &s.b_rate, R));
+    TRY(dalloc(c, &s.b_Ev, R));
+    TRY(dalloc(c, &s.b_Elog, R));
+    TRY(dalloc(c, &s.Tbdirect, R));
+    TRY(dalloc(c, &s.aux, R));
+  }
+  s.update_grid = row_grid(c, R);
+  TRY(dalloc(c, &s.colsum_partial, (size_t)s.update_grid * c->Kp));
+  return 0;
+}
+
+// ---- sweep dispatch ----------------------------------------------------------
+template <int G, int V> int launch_sweep_gv(hpf_ctx *c, const SweepArgs &a)
+{
+  const uint32_t groups_per_block = kSweepThreads / G;
+  const uint32_t grid = (a.nsegs + groups_per_block - 1) / groups_per_block;
+  if (grid == 0) return 0;
+  if (c->bias) sweep_kernel<G, V, true><<<grid, kSweepThreads, 0, c->stream>>>(a);
+  else sweep_kernel<G, V, false><<<grid, kSweepThreads, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int G> int launch_sweep_g(hpf_ctx *c, const SweepArgs &a)
+{
+  switch (c->sweep_v) {
+  case 1: return launch_sweep_gv<G, 1>(c, a);
+  case 2: return launch_sweep_gv<G, 2>(c, a);
+  case 3: return launch_sweep_gv<G, 3>(c, a);
+  case 4: return launch_sweep_gv<G, 4>(c, a);
+  case 5: return launch_sweep_gv<G, 5>(c, a);
+  case 6: return launch_sweep_gv<G, 6>(c, a);
+  case 7: return launch_sweep_gv<G, 7>(c, a);
+  case 8: return launch_sweep_gv<G, 8>(c, a);
+  }
+  return fail(c, HPF_EINVAL, "unsupported sweep shape G=%d V=%d", G, c->sweep_v);
+}
+
+int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside)
+{
+  SweepArgs a;
+  memset(&a, 0, sizeof a);
+  const WorkList &w = rowside.wl;
+  a.seg = w.seg; a.seg_out = w.seg_out; a.nsegs = w.nsegs; a.R = rowside.R;
+  a.idx = w.idx; a.y = w.y;
+  a.Arow = rowside.A; a.Acol = colside.A;
+  a.T = rowside.T; a.Tpart = rowside.Tpart;
+  a.row_aux = rowside.aux; a.col_aux = colside.aux;
+  a.Tb = rowside.Tb; a.Tbpart = rowside.Tbpart;
+  a.ElogRow = rowside.Elog; a.ElogCol = colside.Elog;
+  a.ElogbRow = rowside.b_Elog; a.ElogbCol = colside.b_Elog;
+  a.Tdirect = rowside.Tdirect; a.Tbdirect = rowside.Tbdirect;
+  a.direct_flag = rowside.direct_flag; a.slow_count = c->slow_count;
+  a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4;
+  switch (c->sweep_g) {
+  case 1: return launch_sweep_g<1>(c, a);
+  case 2: return launch_sweep_g<2>(c, a);
+  case 4: return launch_sweep_g<4>(c, a);
+  case 8: return launch_sweep_g<8>(c, a);
+  case 16: return launch_sweep_g<16>(c, a);
+  case 32: return launch_sweep_g<32>(c, a);
+  }
+  return fail(c, HPF_EINVAL, "unsupported sweep group %d", c->sweep_g);
+}
+
+int launch_combine(hpf_ctx *c, Side &s)
+{
+  if (s.wl.nmulti == 0) return 0;
+  CombineArgs a;
+  a.multi_row = s.wl.multi_row; a.multi_first = s.wl.multi_first; a.multi_cnt = s.wl.multi_cnt;
+  a.nmulti = s.wl.nmulti; a.Kp = c->Kp; a.Tpart = s.Tpart; a.T = s.T;
+  a.Tbpart = c->bias ? s.Tbpart : nullptr; a.Tb = s.Tb;
+  const size_t sm = ((size_t)kUpdateWarps * c->Kp + kUpdateWarps) * sizeof(float);
+  combine_kernel<<<s.wl.nmulti, kUpdateWarps * 32, sm, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_count)
+{
+  UpdateArgs a;
+  memset(&a, 0, sizeof a);
+  a.R = s.R; a.K = c->K; a.Kp = c->Kp;
+  a.T = s.T; a.Tdirect = s.Tdirect; a.direct_flag = s.direct_flag;
+  a.A = s.A; a.Elog = s.Elog; a.Ev = s.Ev; a.shape = s.shape; a.rate = s.rate; a.shift = s.shift;
+  a.hier = c->hier; a.colsum_other = colsum_other;
+  a.prior_shape = (float)s.prior_shape; a.prior_rate = (float)s.prior_rate;
+  a.pr_shape = s.pr_shape; a.pr_rate = s.pr_rate; a.pr_Ev = s.pr_Ev;
+  a.pr_prior_shape = (float)s.pr_prior_shape; a.pr_prior_rate = (float)s.pr_prior_rate;
+  a.bias = c->bias; a.Tb = s.Tb; a.Tbdirect = s.Tbdirect;
+  a.b_shape = s.b_shape; a.b_rate = s.b_rate; a.b_Ev = s.b_Ev; a.b_Elog = s.b_Elog; a.aux = s.aux;
+  a.bias_prior_shape = (float)s.bias_prior_shape;
+  a.bias_rate_total = (float)(s.bias_prior_rate + bias_count);
+  a.colsum_partial = s.colsum_partial;
+  const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
+  update_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  colsum_finalize_kernel<<<(c->Kp + 127) / 128, 128, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
+                                                                     s.direct_flag);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int refresh_colsum(hpf_ctx *c, Side &s)
+{
+  const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
+  colsum_partial_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(s.Ev, s.R, c->Kp, s.colsum_partial);
+  c->launches++;
+  CU(cudaGetLastError());
+  colsum_finalize_kernel<<<(c->Kp + 127) / 128, 128, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
+                                                                     nullptr);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- work lists ---------------------------------------------------------------
+// Split every row into segments of <= seg_len nonzeros; a row with one segment
+// writes its T row directly, a row with several writes partial slots that
+// combine_kernel adds in order.  Segments are counting-sorted by descending
+// length so that (a) the 32/G segments a warp advances in lock-step have equal
+// trip counts and (b) long work is scheduled first.
+int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, const uint32_t *d_idx, const uint8_t *d_y)
+{
+  WorkList &w = s.wl;
+  dfree(c, w.seg); dfree(c, w.seg_out); dfree(c, w.multi_row); dfree(c, w.multi_first); dfree(c, w.multi_cnt);
+  w = WorkList();
+  w.idx = d_idx; w.y = d_y;
+  const uint32_t R = s.R, L = c->seg_len;
+  uint64_t nsegs64 = 0;
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t len = ptr[r + 1] - ptr[r];
+    nsegs64 += len == 0 ? 1 : (len + L - 1) / L;
+  }
+  if (nsegs64 >= 0xfffffff0ull) return fail(c, HPF_EINVAL, "too many work segments (%llu)", (unsigned long long)nsegs64);
+  const uint32_t nsegs = (uint32_t)nsegs64;
+  std::vector<uint4> seg(nsegs);
+  std::vector<uint32_t> seg_out(nsegs);
+  std::vector<uint32_t> multi_row, multi_first, multi_cnt;
+  // counting sort by length, descending: bucket b holds length L - b
+  std::vector<uint32_t> bucket(L + 2, 0);
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t len = ptr[r + 1] - ptr[r];
+    if (len <= L) bucket[L - (uint32_t)len + 1]++;
+    else {
+      bucket[1] += (uint32_t)(len / L);
+      if (len % L) bucket[L - (uint32_t)(len % L) + 1]++;
+    }
+  }
+  for (uint32_t b = 1; b < L + 2; ++b) bucket[b] += bucket[b - 1];
+  uint32_t nslots = 0;
+  for (uint32_t r = 0; r < R; ++r) {
+    const uint64_t b0 = ptr[r], len = ptr[r + 1] - ptr[r];
+    if (len <= L) {
+      const uint32_t pos = bucket[L - (uint32_t)len]++;
+      seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, (uint32_t)len);
+      seg_out[pos] = r;
+    } else {
+      const uint32_t cnt = (uint32_t)((len + L - 1) / L);
+      multi_row.push_back(r); multi_first.push_back(nslots); multi_cnt.push_back(cnt);
+      for (uint32_t q = 0; q < cnt; ++q) {
+        const uint64_t sb = b0 + (uint64_t)q * L;
+        const uint32_t sl = (uint32_t)std::min<uint64_t>(L, len - (uint64_t)q * L);
+        const uint32_t pos = bucket[L - sl]++;
+        seg[pos] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
+        seg_out[pos] = R + nslots + q;
+      }
+      nslots += cnt;
+    }
+  }
+  w.nsegs = nsegs; w.npartial = nslots; w.nmulti = (uint32_t)multi_row.size();
+  TRY(dalloc(c, &w.seg, nsegs, false));
+  TRY(dalloc(c, &w.seg_out, nsegs, false));
+  CU(cudaMemcpyAsync(w.seg, seg.data(), sizeof(uint4) * nsegs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(w.seg_out, seg_out.data(), sizeof(uint32_t) * nsegs, cudaMemcpyHostToDevice, c->stream));
+  if (w.nmulti) {
+    TRY(dalloc(c, &w.multi_row, w.nmulti, false));
+    TRY(dalloc(c, &w.multi_first, w.nmulti, false));
+    TRY(dalloc(c, &w.multi_cnt, w.nmulti, false));
+    CU(cudaMemcpyAsync(w.multi_row, multi_row.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(w.multi_first, multi_first.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(w.multi_cnt, multi_cnt.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (nslots > s.part_rows_cap) {
+    dfree(c, s.Tpart); dfree(c, s.Tbpart);
+    TRY(dalloc(c, &s.Tpart, (size_t)nslots * c->Kp, false));
+    if (c->bias) TRY(dalloc(c, &s.Tbpart, nslots, false));
+    s.part_rows_cap = nslots;
+  }
+  CU(cudaStreamSynchronize(c->stream)); // host vectors go out of scope
+  return 0;
+}
+
+int ensure_aux(hpf_ctx *c)
+{
+  if (!c->bias || !c->aux_dirty) return 0;
+  build_aux_kernel<<<(c->th.R + 255) / 256, 256, 0, c->stream>>>(c->th.b_Elog, c->th.shift, c->th.R, c->th.aux);
+  build_aux_kernel<<<(c->be.R + 255) / 256, 256, 0, c->stream>>>(c->be.b_Elog, c->be.shift, c->be.R, c->be.aux);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  c->aux_dirty = false;
+  return 0;
+}
+
+// one CAVI iteration; order of hgaprec.cc:1340-1414 (hier), 928-956 (vb),
+// 1227-1297 (vb_bias, both orderings)
+#define MARK(i) do { if (c->profiling) CU(cudaEventRecord(c->pev[i], c->stream)); } while (0)
+
+int one_iteration(hpf_ctx *c)
+{
+  MARK(0);
+  TRY(launch_sweep(c, c->th, c->be)); // user pass  (CSR): T_theta
+  MARK(1);
+  TRY(launch_sweep(c, c->be, c->th)); // item pass  (CSC): T_beta (local users only)
+  MARK(2);
+  TRY(launch_combine(c, c->th));
+  TRY(launch_combine(c, c->be));
+  MARK(3);
+  const double n_glob = c->cfg.n_users_global ? (double)c->cfg.n_users_global : (double)c->cfg.n_users;
+  if (c->jacobi) { // -novb: beta's rate uses the OLD (global) sum_u E[theta], hgaprec.cc:1278-1283
+    if (c->nranks > 1 && !c->th_colsum_global) {
+      int rc = g_nccl.AllReduce(c->th.colsum, c->th.colsum, c->Kp, ncclFloat32, ncclSum, c->comm, c->stream);
+      if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclAllReduce(colsum): %d", rc);
+    }
+    CU(cudaMemcpyAsync(c->colsum_theta_old, c->th.colsum, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  // theta: rate from the old beta column sums (Gauss-Seidel and Jacobi alike)
+  TRY(launch_update(c, c->th, c->be.colsum, (double)c->cfg.n_items));
+  MARK(4);
+  if (c->nranks > 1) {
+    // [T_beta | Tb_beta | colsum_theta] summed over the user shards, in place
+    int rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count, ncclFloat32, ncclSum, c->comm, c->stream);
+    if (rc != ncclSuccess)
+      return fail(c, HPF_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    c->th_colsum_global = true;
+  }
+  // beta: Gauss-Seidel uses the NEW sum_u E[theta] (hgaprec.cc:1380-1384), -novb the old one
+  MARK(5);
+  TRY(launch_update(c, c->be, c->jacobi ? c->colsum_theta_old : c->th.colsum, n_glob));
+  MARK(6);
+  c->iterations++;
+  return 0;
+}
+
+int check_ready(hpf_ctx *c)
+{
+  if (!c->ratings_set) return fail(c, HPF_EINVAL, "hpf_set_ratings_csr has not been called");
+  if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "hpf_set_state(HPF_THETA/HPF_BETA) has not been called");
+  if (c->hier && (!c->th.have_pr || !c->be.have_pr))
+    return fail(c, HPF_EINVAL, "hpf_set_state(HPF_THETARATE/HPF_BETARATE) has not been called");
+  if (c->bias && (!c->th.have_bias || !c->be.have_bias))
+    return fail(c, HPF_EINVAL, "hpf_set_state(HPF_THETABIAS/HPF_BETABIAS) has not been called");
+  return 0;
+}
+
+// upload a host fp64 array into a temporary device buffer
+int stage_in(hpf_ctx *c, const double *host, size_t count, double **dev)
+{
+  void *q = nullptr;
+  CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(double)));
+  *dev = (double *)q;
+  cudaError_t e = cudaMemcpyAsync(q, host, count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) { cudaFree(q); return fail(c, HPF_ECUDA, "H2D copy: %s", cudaGetErrorString(e)); }
+  return 0;
+}
+
+} // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+void hpf_config_default(hpf_config *cfg)
+{
+  memset(cfg, 0, sizeof *cfg);
+  cfg->abi_version = HPF_ABI_VERSION;
+  cfg->theta_shape = cfg->theta_rate = cfg->beta_shape = cfg->beta_rate = 0.3;
+  cfg->thetarate_shape = cfg->thetarate_rate = cfg->betarate_shape = cfg->betarate_rate = 0.3;
+  cfg->thetabias_shape = cfg->thetabias_rate = cfg->betabias_shape = cfg->betabias_rate = 0.3;
+}
+
+const char *hpf_last_error(const hpf_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hpf_create(const hpf_config *cfg, hpf_ctx **out)
+{
+  hpf_ctx *c = nullptr; // CU()/fail() report into the thread-local slot until the ctx exists
+  if (!cfg || !out) return fail(c, HPF_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != HPF_ABI_VERSION) return fail(c, HPF_EINVAL, "abi_version %u != %u", cfg->abi_version, HPF_ABI_VERSION);
+  if (cfg->k == 0 || cfg->k > 1024) return fail(c, HPF_EINVAL, "k=%u out of range [1,1024]", cfg->k);
+  if (cfg->n_items == 0) return fail(c, HPF_EINVAL, "n_items must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(c, HPF_ENODEVICE, "no CUDA device available (libhpf_b200 has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(c, HPF_EINVAL, "device %d not in [0,%d)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  hpf_ctx *n = new hpf_ctx();
+  n->cfg = *cfg;
+  n->K = cfg->k; n->Kp = (cfg->k + 3u) & ~3u; n->K4 = n->Kp / 4;
+  n->hier = cfg->flags & HPF_HIER; n->bias = cfg->flags & HPF_BIAS; n->binary = cfg->flags & HPF_BINARY;
+  n->jacobi = (cfg->flags & HPF_JACOBI) && !n->hier;
+  cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (const char *e = getenv("HPF_SEG_LEN")) { int v = atoi(e); if (v >= 8 && v <= 65536) n->seg_len = v; }
+  pick_sweep_shape(n);
+  c = n;
+  int rc = 0;
+  do {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, HPF_ECUDA, "cudaStreamCreate failed"); break; }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    for (auto &e : c->pev) cudaEventCreate(&e);
+    c->th.prior_shape = cfg->theta_shape; c->th.prior_rate = cfg->theta_rate;
+    c->th.pr_prior_shape = cfg->thetarate_shape; c->th.pr_prior_rate = cfg->thetarate_rate;
+    c->th.bias_prior_shape = cfg->thetabias_shape; c->th.bias_prior_rate = cfg->thetabias_rate;
+    c->be.prior_shape = cfg->beta_shape; c->be.prior_rate = cfg->beta_rate;
+    c->be.pr_prior_shape = cfg->betarate_shape; c->be.pr_prior_rate = cfg->betarate_rate;
+    c->be.bias_prior_shape = cfg->betabias_shape; c->be.bias_prior_rate = cfg->betabias_rate;
+    if ((rc = alloc_side(c, c->th, cfg->n_users))) break;
+    if ((rc = alloc_side(c, c->be, cfg->n_items))) break;
+    // item-side reduce block: [T_beta (m x Kp) | Tb_beta (m, padded to 4) | colsum_theta (Kp)]
+    const size_t mk = (size_t)cfg->n_items * c->Kp, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
+    c->red_count = mk + mpad + c->Kp;
+    if ((rc = dalloc(c, &c->redblock, c->red_count))) break;
+    c->be.T = c->redblock;
+    c->be.Tb = c->bias ? c->redblock + mk : nullptr;
+    c->th.colsum = c->redblock + mk + mpad;
+    if ((rc = dalloc(c, &c->be.colsum, c->Kp))) break;
+    if ((rc = dalloc(c, &c->th.T, (size_t)cfg->n_users * c->Kp))) break;
+    if (c->bias && (rc = dalloc(c, &c->th.Tb, cfg->n_users))) break;
+    if ((rc = dalloc(c, &c->colsum_theta_old, c->Kp))) break;
+    if ((rc = dalloc(c, &c->slow_count, 1))) break;
+    if ((rc = dalloc(c, &c->logfact, 256))) break;
+    if ((rc = dalloc(c, &c->ll_blocks, (size_t)c->sm_count * 8))) break;
+    if ((rc = dalloc(c, &c->ll_out, 1))) break;
+    double lf[256];
+    lf[0] = lf[1] = log(1.0);
+    for (int v = 2; v < 256; ++v) lf[v] = lf[v - 1] + log((double)v); // log_factorial, hgaprec.cc:1563-1570
+    if (cudaMemcpyAsync(c->logfact, lf, sizeof lf, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(c, HPF_ECUDA, "initial upload failed"); break; }
+  } while (0);
+  if (rc != 0) {
+    g_create_error = c->err.empty() ? g_create_error : c->err;
+    hpf_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+void hpf_destroy(hpf_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (void *p : c->allocs) cudaFree(p);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  for (auto &e : c->pev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col_idx, const uint8_t *y)
+{
+  if (!c || !row_ptr) return fail(c, HPF_EINVAL, "null argument");
+  CU(cudaSetDevice(c->cfg.device));
+  const uint32_t n = c->cfg.n_users, m = c->cfg.n_items;
+  const uint64_t nnz = row_ptr[n];
+  if (row_ptr[0] != 0) return fail(c, HPF_EINVAL, "row_ptr[0] must be 0");
+  for (uint32_t r = 0; r < n; ++r)
+    if (row_ptr[r + 1] < row_ptr[r]) return fail(c, HPF_EINVAL, "row_ptr not monotone at row %u", r);
+  if (nnz > 0 && !col_idx) return fail(c, HPF_EINVAL, "col_idx is null");
+  if (nnz >= 0xffffffffull) return fail(c, HPF_EINVAL, "nnz=%llu per ctx exceeds 2^32-1", (unsigned long long)nnz);
+  for (uint64_t j = 0; j < nnz; ++j)
+    if (col_idx[j] >= m) return fail(c, HPF_EINVAL, "col_idx[%llu]=%u >= n_items=%u", (unsigned long long)j, col_idx[j], m);
+  dfree(c, c->csr_idx); dfree(c, c->csc_idx); dfree(c, c->csr_y); dfree(c, c->csc_y);
+  c->csr_idx = c->csc_idx = nullptr; c->csr_y = c->csc_y = nullptr;
+  c->nnz = nnz;
+  TRY(dalloc(c, &c->csr_idx, nnz, false));
+  TRY(dalloc(c, &c->csc_idx, nnz, false));
+  if (y) { TRY(dalloc(c, &c->csr_y, nnz, false)); TRY(dalloc(c, &c->csc_y, nnz, false)); }
+  std::vector<uint64_t> col_ptr(m + 1, 0);
+  if (nnz > 0) {
+    CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
+    if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
+    // CSC by a stable radix sort of (item, position): rows stay ascending per item
+    uint64_t *d_rowptr = nullptr, *d_colptr = nullptr;
+    uint32_t *d_rowof = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_key2 = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)m) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nnz, 0, end_bit, c->stream);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+    A((void **)&d_rowptr, (n + 1) * 8); A((void **)&d_colptr, ((size_t)m + 1) * 8); A((void **)&d_rowof, nnz * 4);
+    A((void **)&d_pos, nnz * 4); A((void **)&d_pos2, nnz * 4); A((void **)&d_key2, nnz * 4); A(&d_tmp, tmp_bytes);
+    const unsigned nb = (unsigned)((nnz + 255) / 256);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rowptr, row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+      expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
+      iota_kernel<<<nb, 256, 0, c->stream>>>(d_pos, nnz);
+      e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)c->csr_idx, d_key2, (const uint32_t *)d_pos,
+                                          d_pos2, (int64_t)nnz, 0, end_bit, c->stream);
+      gather_csc_kernel<<<nb, 256, 0, c->stream>>>(d_pos2, d_rowof, c->csr_y, nnz, c->csc_idx, c->csc_y);
+      col_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(d_key2, nnz, m, d_colptr);
+      c->launches += 4;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(col_ptr.data(), d_colptr, ((size_t)m + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(d_rowptr); cudaFree(d_colptr); cudaFree(d_rowof); cudaFree(d_pos); cudaFree(d_pos2); cudaFree(d_key2); cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "CSC build: %s", cudaGetErrorString(e));
+  }
+  TRY(build_worklist(c, c->th, row_ptr, c->csr_idx, c->csr_y));
+  TRY(build_worklist(c, c->be, col_ptr.data(), c->csc_idx, c->csc_y));
+  c->ratings_set = true;
+  return 0;
+}
+
+int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate, const double *Ev, const double *Elogv)
+{
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  CU(cudaSetDevice(c->cfg.device));
+  const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
+  Side &s = theta_side ? c->th : c->be;
+  const uint32_t R = s.R, K = c->K, Kp = c->Kp;
+  double *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
+  int rc = 0;
+  switch (which) {
+  case HPF_THETA:
+  case HPF_BETA: {
+    if (!shape || !rate || !Ev || !Elogv) return fail(c, HPF_EINVAL, "THETA/BETA need shape, rate, Ev and Elogv");
+    const size_t rk = (size_t)R * K;
+    const uint32_t g = s.update_grid;
+    if ((rc = stage_in(c, shape, rk, &d0)) || (rc = stage_in(c, rate, c->hier ? rk : K, &d1)) ||
+        (rc = stage_in(c, Ev, rk, &d2)) || (rc = stage_in(c, Elogv, rk, &d3))) break;
+    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d0, R, K, Kp, s.shape, 0.f);
+    if (c->hier) import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d1, R, K, Kp, s.rate, 1.f);
+    else import_matrix_kernel<<<1, kUpdateWarps * 32, 0, c->stream>>>(d1, 1, K, Kp, s.rate, 1.f);
+    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d2, R, K, Kp, s.Ev, 0.f);
+    import_elog_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d3, R, K, Kp, s.Elog, s.A, s.shift);
+    c->launches += 4;
+    if ((rc = refresh_colsum(c, s))) break;
+    s.have_state = true;
+    c->aux_dirty = true;
+    if (theta_side) c->th_colsum_global = false;
+    break;
+  }
+  case HPF_THETARATE:
+  case HPF_BETARATE: {
+    if (!c->hier) return fail(c, HPF_EINVAL, "THETARATE/BETARATE exist only with HPF_HIER");
+    if (!shape || !rate || !Ev) return fail(c, HPF_EINVAL, "THETARATE/BETARATE need shape, rate and Ev");
+    if ((rc = stage_in(c, shape, R, &d0)) || (rc = stage_in(c, rate, R, &d1)) || (rc = stage_in(c, Ev, R, &d2))) break;
+    const unsigned nb = (R + 255) / 256;
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d0, R, s.pr_shape);
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d1, R, s.pr_rate);
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d2, R, s.pr_Ev);
+    c->launches += 3;
+    s.have_pr = true;
+    break;
+  }
+  case HPF_THETABIAS:
+  case HPF_BETABIAS: {
+    if (!c->bias) return fail(c, HPF_EINVAL, "THETABIAS/BETABIAS exist only with HPF_BIAS");
+    if (!shape || !rate || !Ev || !Elogv) return fail(c, HPF_EINVAL, "bias sets need shape, rate, Ev and Elogv");
+    if ((rc = stage_in(c, shape, R, &d0)) || (rc = stage_in(c, rate, R, &d1)) || (rc = stage_in(c, Ev, R, &d2)) ||
+        (rc = stage_in(c, Elogv, R, &d3))) break;
+    const unsigned nb = (R + 255) / 256;
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d0, R, s.b_shape);
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d1, R, s.b_rate);
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d2, R, s.b_Ev);
+    import_vector_kernel<<<nb, 256, 0, c->stream>>>(d3, R, s.b_Elog);
+    c->launches += 4;
+    s.have_bias = true;
+    c->aux_dirty = true;
+    break;
+  }
+  default:
+    return fail(c, HPF_EINVAL, "unknown parameter id %d", which);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d0); cudaFree(d1); cudaFree(d2); cudaFree(d3);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_set_state: %s", cudaGetErrorString(e));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_set_state: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev, double *Elogv)
+{
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  CU(cudaSetDevice(c->cfg.device));
+  const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
+  Side &s = theta_side ? c->th : c->be;
+  const uint32_t R = s.R, K = c->K, Kp = c->Kp;
+  double *stage = nullptr;
+  const size_t rk = (size_t)R * K;
+  CU(cudaMalloc((void **)&stage, std::max<size_t>(rk, 16) * sizeof(double)));
+  cudaError_t e = cudaSuccess;
+  auto out_matrix = [&](const float *src, double *dst, uint32_t rows) {
+    if (!dst || e != cudaSuccess) return;
+    export_matrix_kernel<<<row_grid(c, rows), kUpdateWarps * 32, 0, c->stream>>>(src, rows, K, Kp, stage);
+    c->launches++;
+    e = cudaMemcpyAsync(dst, stage, (size_t)rows * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  };
+  auto out_vector = [&](const float *src, double *dst) {
+    if (!dst || e != cudaSuccess) return;
+    export_vector_kernel<<<(R + 255) / 256, 256, 0, c->stream>>>(src, R, stage);
+    c->launches++;
+    e = cudaMemcpyAsync(dst, stage, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  };
+  int rc = 0;
+  switch (which) {
+  case HPF_THETA:
+  case HPF_BETA:
+    out_matrix(s.shape, shape, R);
+    out_matrix(s.rate, rate, c->hier ? R : 1);
+    out_matrix(s.Ev, Ev, R);
+    out_matrix(s.Elog, Elogv, R);
+    break;
+  case HPF_THETARATE:
+  case HPF_BETARATE:
+    if (!c->hier) { rc = fail(c, HPF_EINVAL, "THETARATE/BETARATE exist only with HPF_HIER"); break; }
+    out_vector(s.pr_shape, shape);
+    out_vector(s.pr_rate, rate);
+    out_vector(s.pr_Ev, Ev);
+    if (Elogv && e == cudaSuccess) {
+      export_gparray_elog_kernel<<<(R + 255) / 256, 256, 0, c->stream>>>(s.pr_shape, s.pr_rate, R, stage);
+      c->launches++;
+      e = cudaMemcpyAsync(Elogv, stage, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    break;
+  case HPF_THETABIAS:
+  case HPF_BETABIAS:
+    if (!c->bias) { rc = fail(c, HPF_EINVAL, "THETABIAS/BETABIAS exist only with HPF_BIAS"); break; }
+    out_vector(s.b_shape, shape);
+    out_vector(s.b_rate, rate);
+    out_vector(s.b_Ev, Ev);
+    out_vector(s.b_Elog, Elogv);
+    break;
+  default:
+    rc = fail(c, HPF_EINVAL, "unknown parameter id %d", which);
+  }
+  cudaFree(stage);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_get_state: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
+{
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  CU(cudaSetDevice(c->cfg.device));
+  TRY(check_ready(c));
+  TRY(ensure_aux(c));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  for (uint32_t it = 0; it < n_iters; ++it) TRY(one_iteration(c));
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  return 0;
+}
+
+int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
+{
+  if (!c || !out) return fail(c, HPF_EINVAL, "null argument");
+  memset(out, 0, sizeof *out);
+  if (n_iters == 0) return 0;
+  CU(cudaSetDevice(c->cfg.device));
+  TRY(check_ready(c));
+  TRY(ensure_aux(c));
+  float acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+  for (uint32_t it = 0; it < n_iters; ++it) {
+    c->profiling = true;
+    int rc = one_iteration(c);
+    c->profiling = false;
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 6; ++i) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
+      acc[i] += ms;
+    }
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->pev[0], c->pev[6]));
+    acc[6] += ms;
+  }
+  CU(cudaGetLastError());
+  const float inv = 1.f / (float)n_iters;
+  out->sweep_user_ms = acc[0] * inv; out->sweep_item_ms = acc[1] * inv; out->combine_ms = acc[2] * inv;
+  out->update_theta_ms = acc[3] * inv; out->allreduce_ms = acc[4] * inv; out->update_beta_ms = acc[5] * inv;
+  out->total_ms = acc[6] * inv;
+  return 0;
+}
+
+int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const uint8_t *y, uint64_t npairs, double *sum_ll)
+{
+  if (!c || !sum_ll) return fail(c, HPF_EINVAL, "null argument");
+  *sum_ll = 0.0;
+  if (npairs == 0) return 0;
+  if (!u || !i || !y) return fail(c, HPF_EINVAL, "null pair arrays");
+  CU(cudaSetDevice(c->cfg.device));
+  if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
+  for (uint64_t p = 0; p < npairs; ++p)
+    if (u[p] >= c->th.R || i[p] >= c->be.R) return fail(c, HPF_EINVAL, "pair %llu out of range", (unsigned long long)p);
+  uint32_t *du = nullptr, *di = nullptr;
+  uint8_t *dy = nullptr;
+  cudaError_t e = cudaMalloc((void **)&du, npairs * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&di, npairs * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dy, npairs);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(du, u, npairs * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(di, i, npairs * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, npairs, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    HeldoutArgs a;
+    a.u = du; a.i = di; a.y = dy; a.npairs = npairs;
+    a.Et = c->th.Ev; a.Eb = c->be.Ev;
+    a.Etb = c->bias ? c->th.b_Ev : nullptr; a.Ebb = c->bias ? c->be.b_Ev : nullptr;
+    a.K4 = c->K4; a.binary = c->binary; a.logfact = c->logfact; a.block_sums = c->ll_blocks;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * 8, (npairs * 8 + kSweepThreads - 1) / kSweepThreads);
+    // fixed mapping: 8 lanes per pair, up to 8 float4 per lane covers K <= 256; wider K uses 32 lanes
+    if (c->K4 <= 64) heldout_kernel<8, 8><<<grid, kSweepThreads, 0, c->stream>>>(a);
+    else heldout_kernel<32, 8><<<grid, kSweepThreads, 0, c->stream>>>(a);
+    sum_blocks_kernel<<<1, 32, 0, c->stream>>>(c->ll_blocks, grid, c->ll_out);
+    c->launches += 2;
+    e = cudaMemcpyAsync(sum_ll, c->ll_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(du); cudaFree(di); cudaFree(dy);
+  if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_heldout_loglik: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int hpf_topn(hpf_ctx *c, const uint32_t *, uint32_t, const uint64_t *, const uint32_t *, uint32_t, uint32_t *, float *)
+{
+  return fail(c, HPF_EINVAL, "hpf_topn: not implemented in this build");
+}
+
+int hpf_comm_unique_id(void *id_out, size_t id_bytes)
+{
+  std::string err;
+  if (!id_out || id_bytes < sizeof(ncclUniqueId)) return fail(nullptr, HPF_EINVAL, "id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+  if (!g_nccl.load(err)) return fail(nullptr, HPF_ENCCL, "%s", err.c_str());
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(nullptr, HPF_ENCCL, "ncclGetUniqueId failed");
+  memcpy(id_out, &id, sizeof id);
+  return 0;
+}
+
+int hpf_comm_init(hpf_ctx *c, int rank, int nranks, const void *id, size_t id_bytes)
+{
+  if (!c || !id || id_bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(c, HPF_EINVAL, "bad communicator arguments");
+  CU(cudaSetDevice(c->cfg.device));
+  std::string err;
+  if (!g_nccl.load(err)) return fail(c, HPF_ENCCL, "%s", err.c_str());
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  int rc = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
+  if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  c->rank = rank; c->nranks = nranks;
+  return 0;
+}
+
+int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
+{
+  if (!c || !out) return HPF_EINVAL;
+  memset(out, 0, sizeof *out);
+  out->kernel_launches = c->launches;
+  out->iterations = c->iterations;
+  unsigned long long sc = 0;
+  cudaSetDevice(c->cfg.device);
+  cudaMemcpy(&sc, c->slow_count, sizeof sc, cudaMemcpyDeviceToHost);
+  out->slow_path_nnz = sc;
+  out->nnz = c->nnz;
+  out->device_bytes = c->device_bytes;
+  out->last_iterate_ms = c->last_ms;
+  out->sweep_group = c->sweep_g;
+  out->sweep_vec = c->sweep_v;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,679 @@
+// hpf_kernels.cuh -- sm_100a device code of the HPF CAVI engine.
+//
+// Formulation.  The reference forms, per nonzero (u,i,y),
+//   phi_k = exp(Elog theta_uk + Elog beta_ik - logsumexp_k')      hgaprec.cc:206-239,
+//                                                                 matrix.hh:367-389
+// and adds y*phi to both shape rows (gpbase.hh:175-180).  Softmax of a SUM of
+// logs is a normalised PRODUCT, so with A_uk = exp(Elog theta_uk - M_u) and
+// B_ik = exp(Elog beta_ik - M_i) (row-max shifted, computed once per iteration
+// in the dense row update):
+//   Z_ui      = sum_k A_uk B_ik            (one dot product, no transcendental)
+//   S^theta_uk = prior + A_uk * sum_i (y_ui / Z_ui) B_ik
+//   S^beta_ik  = prior + B_ik * sum_u (y_ui / Z_ui) A_uk
+// The two sums are the SAME kernel run over the CSR (rows = users, gathering
+// item rows) and over the CSC (rows = items, gathering user rows): every
+// accumulator lives in registers, there are no global atomics and the result
+// is deterministic.  A nonzero whose Z under/overflows in fp32 takes an exact
+// log-domain fallback (sweep_slow_path) that adds y*phi straight into a side
+// buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace hpf {
+
+constexpr int kSweepThreads = 256;
+constexpr int kUpdateWarps = 8;
+constexpr float kZMin = 1e-30f;
+constexpr float kZMax = 1e30f;
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// streaming (read-once) loads: keep them out of L1 so the gathered factor rows stay
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u8(const uint8_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// digamma for x > 0 in fp32: upward recurrence to x >= 6, then the Stirling
+// series.  Replaces gsl_sf_psi at gpbase.hh:260,593,923.
+__device__ __forceinline__ float digammaf(float x)
+{
+  float r = 0.f;
+  while (x < 6.f) {
+    r -= 1.f / x;
+    x += 1.f;
+  }
+  const float f = 1.f / (x * x);
+  const float t = f * (-1.f / 12.f + f * (1.f / 120.f + f * (-1.f / 252.f + f * (1.f / 240.f))));
+  return r + logf(x) - 0.5f / x + t;
+}
+
+// ---------------------------------------------------------------------------
+// K1: phi sweep.  One GROUP of G lanes owns one work segment (<= seg_len
+// consecutive nonzeros of ONE row); 32/G segments advance in lock-step per warp.
+// Lane g of a group holds float4 #(g + v*G), v < V, of the row-side factor row
+// and of the accumulator; per nonzero the group gathers the column-side row with
+// 128-bit loads, forms Z with a G-lane xor-shuffle reduction and accumulates
+// (y/Z) * B.  Replaces hgaprec.cc:1340-1366 / 928-942 / 1227-1248.
+// ---------------------------------------------------------------------------
+struct SweepArgs {
+  const uint4 *seg;        // {begin_lo, begin_hi, row, len}
+  const uint32_t *seg_out; // < R: row of T;  >= R: slot (out - R) of Tpart
+  uint32_t nsegs;
+  uint32_t R;              // rows on the row side
+  const uint32_t *idx;     // per nonzero: row number on the column side
+  const uint8_t *y;        // per nonzero rating, or nullptr (all ones)
+  const float *Arow;       // [R x Kp]  exp(Elog - shift), row side
+  const float *Acol;       // [C x Kp]  same, column side
+  float *T;                // [R x Kp]  out: sum (y/Z) * Acol
+  float *Tpart;            // [P x Kp]  out: partial sums of multi-segment rows
+  // -bias (phi has K+2 slots, hgaprec.cc:222-239)
+  const float2 *row_aux;   // {exp(Elogbias_r - shift_r), exp(-shift_r)}
+  const float2 *col_aux;
+  float *Tb;               // [R] out: sum (y/Z) * col_aux.y
+  float *Tbpart;           // [P]
+  // exact fallback
+  const float *ElogRow, *ElogCol;   // [. x Kp], padding = -inf
+  const float *ElogbRow, *ElogbCol; // bias logs (or nullptr)
+  float *Tdirect;          // [R x Kp] += y*phi
+  float *Tbdirect;         // [R]
+  uint32_t *direct_flag;   // set to 1 when Tdirect was touched
+  unsigned long long *slow_count;
+  uint32_t K, Kp, K4;
+};
+
+template <int G>
+__device__ __forceinline__ uint32_t group_mask(int lane)
+{
+  if (G == 32) return 0xffffffffu;
+  return ((1u << G) - 1u) << (lane & ~(G - 1));
+}
+
+// Exact log-domain phi for one nonzero (called when Z left the fp32 range):
+// phi_k = exp(x_k - max) / sum, x_k = ElogRow_k + ElogCol_k (+ the two bias
+// logs), i.e. what get_phi + lognormalize compute; y*phi is added to Tdirect.
+struct SlowArgs { // by value: taking the address of kernel parameters would force a local copy
+  const float *ElogRow, *ElogCol, *ElogbRow, *ElogbCol;
+  float *Tdirect, *Tbdirect;
+  uint32_t *direct_flag;
+  unsigned long long *slow_count;
+  uint32_t K, Kp, K4;
+};
+
+template <int G, int V, bool BIAS>
+__device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uint32_t c, float yv, int lane)
+{
+  const int gl = lane & (G - 1);
+  const uint32_t mask = group_mask<G>(lane);
+  const float4 *er = reinterpret_cast<const float4 *>(a.ElogRow) + (size_t)row * a.K4;
+  const float4 *ec = reinterpret_cast<const float4 *>(a.ElogCol) + (size_t)c * a.K4;
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint32_t q = gl + v * G;
+    if (q < a.K4) {
+      const float4 r4 = er[q], c4 = ec[q];
+      mx = fmaxf(mx, fmaxf(fmaxf(r4.x + c4.x, r4.y + c4.y), fmaxf(r4.z + c4.z, r4.w + c4.w)));
+    }
+  }
+  float xbr = -CUDART_INF_F, xbc = -CUDART_INF_F;
+  if (BIAS) {
+    xbr = a.ElogbRow[row];
+    xbc = a.ElogbCol[c];
+    mx = fmaxf(mx, fmaxf(xbr, xbc));
+  }
+#pragma unroll
+  for (int off = G / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(mask, mx, off));
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint32_t q = gl + v * G;
+    if (q < a.K4) {
+      const float4 r4 = er[q], c4 = ec[q];
+      sum += expf(r4.x + c4.x - mx) + expf(r4.y + c4.y - mx) + expf(r4.z + c4.z - mx) + expf(r4.w + c4.w - mx);
+    }
+  }
+  if (BIAS && gl == 0) sum += expf(xbr - mx) + expf(xbc - mx);
+#pragma unroll
+  for (int off = G / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(mask, sum, off);
+  const float sc = yv / sum;
+  float *td = a.Tdirect + (size_t)row * a.Kp;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint32_t q = gl + v * G;
+    if (q < a.K4) {
+      const float4 r4 = er[q], c4 = ec[q];
+      const uint32_t k0 = q * 4;
+      if (k0 + 0 < a.K) atomicAdd(td + k0 + 0, sc * expf(r4.x + c4.x - mx));
+      if (k0 + 1 < a.K) atomicAdd(td + k0 + 1, sc * expf(r4.y + c4.y - mx));
+      if (k0 + 2 < a.K) atomicAdd(td + k0 + 2, sc * expf(r4.z + c4.z - mx));
+      if (k0 + 3 < a.K) atomicAdd(td + k0 + 3, sc * expf(r4.w + c4.w - mx));
+    }
+  }
+  if (gl == 0) {
+    if (BIAS) atomicAdd(a.Tbdirect + row, sc * expf(xbr - mx));
+    atomicAdd(a.slow_count, 1ull);
+    *a.direct_flag = 1u;
+  }
+}
+
+template <int G, int V, bool BIAS>
+__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const uint32_t group = (blockIdx.x * (uint32_t)kSweepThreads + threadIdx.x) / G;
+  const bool have = group < a.nsegs;
+
+  uint64_t begin = 0;
+  uint32_t row = 0, len = 0, out = 0;
+  if (have) {
+    const uint4 s = __ldg(a.seg + group);
+    begin = (uint64_t)s.x | ((uint64_t)s.y << 32);
+    row = s.z;
+    len = s.w;
+    out = __ldg(a.seg_out + group);
+  }
+
+  float4 ar[V], acc[V];
+  {
+    const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.K4;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const uint32_t q = gl + v * G;
+      ar[v] = (have && q < a.K4) ? ldg4(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float2 raux = make_float2(0.f, 0.f);
+  float accb = 0.f;
+  if (BIAS && have) raux = __ldg(a.row_aux + row);
+
+  const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+  const uint32_t *ip = a.idx + begin;
+  const uint8_t *yp = a.y ? a.y + begin : nullptr;
+  const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
+
+  uint32_t cbuf = 0, ybuf = 1;
+  for (uint32_t j = 0; j < maxlen; ++j) {
+    if ((j & (G - 1)) == 0) {
+      const uint32_t jj = j + gl;
+      cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u;
+      ybuf = (yp != nullptr && jj < len) ? ld_stream_u8(yp + jj) : 1u;
+    }
+    const uint32_t c = __shfl_sync(0xffffffffu, cbuf, j & (G - 1), G);
+    const uint32_t yv = __shfl_sync(0xffffffffu, ybuf, j & (G - 1), G);
+    const bool active = j < len;
+
+    float4 b[V];
+    const float4 *cp = acol + (size_t)c * a.K4;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const uint32_t q = gl + v * G;
+      b[v] = (active && q < a.K4) ? ldg4(cp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float2 caux = make_float2(0.f, 0.f);
+    if (BIAS && active) caux = __ldg(a.col_aux + c);
+
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      dot = fmaf(ar[v].x, b[v].x, dot);
+      dot = fmaf(ar[v].y, b[v].y, dot);
+      dot = fmaf(ar[v].z, b[v].z, dot);
+      dot = fmaf(ar[v].w, b[v].w, dot);
+    }
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    float z = dot;
+    if (BIAS) z += raux.x * caux.y + caux.x * raux.y;
+
+    if (active) {
+      if (z > kZMin && z < kZMax) {
+        const float sc = (float)yv / z;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc[v].x = fmaf(sc, b[v].x, acc[v].x);
+          acc[v].y = fmaf(sc, b[v].y, acc[v].y);
+          acc[v].z = fmaf(sc, b[v].z, acc[v].z);
+          acc[v].w = fmaf(sc, b[v].w, acc[v].w);
+        }
+        if (BIAS) accb = fmaf(sc, caux.y, accb);
+      } else {
+        SlowArgs sa;
+        sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
+        sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
+        sa.slow_count = a.slow_count; sa.K = a.K; sa.Kp = a.Kp; sa.K4 = a.K4;
+        sweep_slow_path<G, V, BIAS>(sa, row, c, (float)yv, lane);
+      }
+    }
+  }
+
+  if (have) {
+    float4 *dst = reinterpret_cast<float4 *>(out < a.R ? a.T + (size_t)out * a.Kp
+                                                        : a.Tpart + (size_t)(out - a.R) * a.Kp);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const uint32_t q = gl + v * G;
+      if (q < a.K4) dst[q] = acc[v];
+    }
+    if (BIAS && gl == 0) {
+      if (out < a.R) a.Tb[out] = accb;
+      else a.Tbpart[out - a.R] = accb;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// combine the partial sums of rows that were split over several segments
+// (fixed order => deterministic).  One block per multi-segment row.
+// ---------------------------------------------------------------------------
+struct CombineArgs {
+  const uint32_t *multi_row, *multi_first, *multi_cnt;
+  uint32_t nmulti, Kp;
+  const float *Tpart;
+  float *T;
+  const float *Tbpart; // or nullptr
+  float *Tb;
+};
+
+__global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const CombineArgs a)
+{
+  extern __shared__ float sm[]; // [kUpdateWarps][Kp] (+ kUpdateWarps for bias)
+  const uint32_t r = blockIdx.x;
+  if (r >= a.nmulti) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row = a.multi_row[r], first = a.multi_first[r], cnt = a.multi_cnt[r];
+  float *mine = sm + (size_t)w * a.Kp;
+  for (uint32_t k = lane; k < a.Kp; k += 32) {
+    float s = 0.f;
+    for (uint32_t p = w; p < cnt; p += kUpdateWarps) s += a.Tpart[(size_t)(first + p) * a.Kp + k];
+    mine[k] = s;
+  }
+  float *smb = sm + (size_t)kUpdateWarps * a.Kp;
+  if (a.Tbpart != nullptr && lane == 0) {
+    float s = 0.f;
+    for (uint32_t p = w; p < cnt; p += kUpdateWarps) s += a.Tbpart[first + p];
+    smb[w] = s;
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kUpdateWarps; ++q) s += sm[(size_t)q * a.Kp + k];
+    a.T[(size_t)row * a.Kp + k] = s;
+  }
+  if (a.Tbpart != nullptr && threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kUpdateWarps; ++q) s += smb[q];
+    a.Tb[row] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2/K3/K4/K5: dense row update, one warp per row.  Fuses, for one parameter
+// matrix: shape = prior + A*T (the add_slice sums), rate (set_prior_rate +
+// update_rate_next, gpbase.hh:163-173,218-223 / GR 560-564), swap (240-246),
+// compute_expectations (248-262), sum_rows / sum_cols (264-280), the GPArray
+// xi/eta step (hgaprec.cc:1398-1414, gpbase.hh:877-925), the bias step
+// (hgaprec.cc:1388-1396) and the next iteration's shifted exponentials.
+// ---------------------------------------------------------------------------
+struct UpdateArgs {
+  uint32_t R, K, Kp;
+  const float *T;
+  float *Tdirect;
+  const uint32_t *direct_flag;
+  float *A, *Elog, *Ev, *shape, *rate; // rate: [R x Kp] (hier) or [Kp] (global rate)
+  float *shift;                        // [R]
+  int hier;
+  const float *colsum_other; // [Kp]  sum over the OTHER side's rows of Ev
+  float prior_shape, prior_rate;
+  float *pr_shape, *pr_rate, *pr_Ev;   // GPArray xi / eta (hier)
+  float pr_prior_shape, pr_prior_rate;
+  int bias;
+  const float *Tb;
+  float *Tbdirect;
+  float *b_shape, *b_rate, *b_Ev, *b_Elog;
+  float2 *aux;
+  float bias_prior_shape, bias_rate_total; // rate prior + (m or n_global)
+  float *colsum_partial;               // [gridDim.x x Kp]
+};
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+__device__ __forceinline__ float floor30(float v) { return v > 0.f ? v : 1e-30f; } // make_nonzero, gpbase.hh:27-44
+
+__global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateArgs a)
+{
+  extern __shared__ float cs[]; // [kUpdateWarps][Kp] column partial sums of Ev
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *mycs = cs + (size_t)w * a.Kp;
+  for (uint32_t k = lane; k < a.Kp; k += 32) mycs[k] = 0.f;
+  const bool use_direct = *a.direct_flag != 0u;
+  const uint32_t warps_total = gridDim.x * kUpdateWarps;
+
+  // the global-rate (GPMatrixGR) vector is written once, by block 0
+  if (!a.hier && blockIdx.x == 0)
+    for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x)
+      a.rate[k] = k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f;
+
+  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < a.R; r += warps_total) {
+    const size_t base = (size_t)r * a.Kp;
+    const float rprior = a.hier ? a.pr_Ev[r] : a.prior_rate;
+    float mx = -CUDART_INF_F, rowsum = 0.f;
+    for (uint32_t k = lane; k < a.Kp; k += 32) {
+      if (k < a.K) {
+        float s = a.prior_shape + a.A[base + k] * a.T[base + k];
+        if (use_direct) {
+          s += a.Tdirect[base + k];
+          a.Tdirect[base + k] = 0.f;
+        }
+        const float rt = rprior + a.colsum_other[k];
+        const float sa = floor30(s), rb = floor30(rt);
+        const float ev = sa / rb;
+        const float el = digammaf(sa) - logf(rb);
+        a.shape[base + k] = s;
+        if (a.hier) a.rate[base + k] = rt;
+        a.Ev[base + k] = ev;
+        a.Elog[base + k] = el;
+        mx = fmaxf(mx, el);
+        rowsum += ev;
+        mycs[k] += ev;
+      } else {
+        a.shape[base + k] = 0.f;
+        if (a.hier) a.rate[base + k] = 1.f;
+        a.Ev[base + k] = 0.f;
+        a.Elog[base + k] = -CUDART_INF_F;
+      }
+    }
+    mx = warp_max(mx);
+    rowsum = warp_sum(rowsum);
+    for (uint32_t k = lane; k < a.Kp; k += 32)
+      a.A[base + k] = k < a.K ? expf(a.Elog[base + k] - mx) : 0.f;
+    if (lane == 0) {
+      a.shift[r] = mx;
+      if (a.hier) {
+        // hgaprec.cc:1399-1405: shape = a' + K a', rate = b' + sum_k E[theta_uk]
+        const float ps = a.pr_prior_shape + (float)a.K * a.pr_prior_shape;
+        const float pr = a.pr_prior_rate + rowsum;
+        a.pr_shape[r] = ps;
+        a.pr_rate[r] = pr;
+        a.pr_Ev[r] = floor30(ps) / floor30(pr);
+      }
+      if (a.bias) {
+        float bs = a.bias_prior_shape + a.aux[r].x * a.Tb[r];
+        if (use_direct) {
+          bs += a.Tbdirect[r];
+          a.Tbdirect[r] = 0.f;
+        }
+        const float br = a.bias_rate_total;
+        const float sa = floor30(bs), rb = floor30(br);
+        const float bel = digammaf(sa) - logf(rb);
+        a.b_shape[r] = bs;
+        a.b_rate[r] = br;
+        a.b_Ev[r] = sa / rb;
+        a.b_Elog[r] = bel;
+        a.aux[r] = make_float2(expf(bel - mx), expf(-mx));
+      }
+    }
+  }
+  __syncthreads();
+  float *dst = a.colsum_partial + (size_t)blockIdx.x * a.Kp;
+  for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kUpdateWarps; ++q) s += cs[(size_t)q * a.Kp + k];
+    dst[k] = s;
+  }
+}
+
+// colsum[k] = sum over blocks of partial[b][k], accumulated in double, fixed
+// order; also clears the side's direct_flag for the next iteration.
+__global__ void colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
+                                       float *colsum, uint32_t *direct_flag)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < Kp) {
+    double s = 0.0;
+    for (uint32_t b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * Kp + k];
+    colsum[k] = (float)s;
+  }
+  if (direct_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *direct_flag = 0u;
+}
+
+// column sums of an existing Ev matrix (after hpf_set_state)
+__global__ void __launch_bounds__(kUpdateWarps * 32) colsum_partial_kernel(const float *Ev, uint32_t R, uint32_t Kp,
+                                                                          float *partial)
+{
+  extern __shared__ float cs[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *mycs = cs + (size_t)w * Kp;
+  for (uint32_t k = lane; k < Kp; k += 32) mycs[k] = 0.f;
+  const uint32_t warps_total = gridDim.x * kUpdateWarps;
+  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
+    for (uint32_t k = lane; k < Kp; k += 32) mycs[k] += Ev[(size_t)r * Kp + k];
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kUpdateWarps; ++q) s += cs[(size_t)q * Kp + k];
+    partial[(size_t)blockIdx.x * Kp + k] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// state import / export (host fp64 row-major, stride K  <->  device fp32, stride Kp)
+// ---------------------------------------------------------------------------
+// matrix import; when Elog != nullptr also derives shift and A in double.
+__global__ void __launch_bounds__(kUpdateWarps * 32) import_matrix_kernel(const double *src, uint32_t R, uint32_t K, uint32_t Kp,
+                                                                         float *dst, float pad)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * kUpdateWarps;
+  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
+    for (uint32_t k = lane; k < Kp; k += 32)
+      dst[(size_t)r * Kp + k] = k < K ? (float)src[(size_t)r * K + k] : pad;
+}
+
+__global__ void __launch_bounds__(kUpdateWarps * 32) import_elog_kernel(const double *src, uint32_t R, uint32_t K, uint32_t Kp,
+                                                                       float *Elog, float *A, float *shift)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * kUpdateWarps;
+  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total) {
+    double mx = -CUDART_INF;
+    for (uint32_t k = lane; k < K; k += 32) mx = fmax(mx, src[(size_t)r * K + k]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    // the stored shift is the fp32 value the sweep's aux terms are built from
+    const float mxf = (float)mx;
+    for (uint32_t k = lane; k < Kp; k += 32) {
+      if (k < K) {
+        const double e = src[(size_t)r * K + k];
+        Elog[(size_t)r * Kp + k] = (float)e;
+        A[(size_t)r * Kp + k] = (float)exp(e - (double)mxf);
+      } else {
+        Elog[(size_t)r * Kp + k] = -CUDART_INF_F;
+        A[(size_t)r * Kp + k] = 0.f;
+      }
+    }
+    if (lane == 0) shift[r] = mxf;
+  }
+}
+
+__global__ void import_vector_kernel(const double *src, uint32_t n, float *dst)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+// aux[r] = {exp(Elogbias_r - shift_r), exp(-shift_r)} from uploaded state
+__global__ void build_aux_kernel(const float *b_Elog, const float *shift, uint32_t R, float2 *aux)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) aux[r] = make_float2(expf(b_Elog[r] - shift[r]), expf(-shift[r]));
+}
+
+__global__ void __launch_bounds__(kUpdateWarps * 32) export_matrix_kernel(const float *src, uint32_t R, uint32_t K, uint32_t Kp,
+                                                                         double *dst)
+{
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warps_total = gridDim.x * kUpdateWarps;
+  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
+    for (uint32_t k = lane; k < K; k += 32) dst[(size_t)r * K + k] = (double)src[(size_t)r * Kp + k];
+}
+
+__global__ void export_vector_kernel(const float *src, uint32_t n, double *dst)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+
+// Elog of a GPArray (xi / eta) is only materialised on export: psi(shape) - log(rate)
+__global__ void export_gparray_elog_kernel(const float *shape, const float *rate, uint32_t n, double *dst)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)(digammaf(floor30(shape[i])) - logf(floor30(rate[i])));
+}
+
+// ---------------------------------------------------------------------------
+// K6: held-out log-likelihood (hgaprec.cc:1439-1470, 1503-1570).  One group of
+// G lanes per (u, i, y) triple; fp32 dot product, fp64 log-likelihood and sum.
+// ---------------------------------------------------------------------------
+struct HeldoutArgs {
+  const uint32_t *u, *i;
+  const uint8_t *y;
+  uint64_t npairs;
+  const float *Et, *Eb;   // Ev matrices [. x Kp]
+  const float *Etb, *Ebb; // bias Ev (or nullptr)
+  uint32_t K4;
+  int binary;
+  const double *logfact;  // [256]  log(y!) as the reference sums it (hgaprec.cc:1563-1570)
+  double *block_sums;     // [gridDim.x]
+};
+
+template <int G, int V>
+__global__ void __launch_bounds__(kSweepThreads) heldout_kernel(const HeldoutArgs a)
+{
+  __shared__ double wsum[kSweepThreads / 32];
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), w = threadIdx.x >> 5;
+  const uint64_t groups_total = (uint64_t)gridDim.x * kSweepThreads / G;
+  double local = 0.0;
+  const uint64_t g0 = ((uint64_t)blockIdx.x * kSweepThreads + threadIdx.x) / G;
+  const uint64_t rounds = (a.npairs + groups_total - 1) / groups_total;
+  for (uint64_t rd = 0; rd < rounds; ++rd) {
+    const uint64_t p = g0 + rd * groups_total;
+    const bool active = p < a.npairs;
+    const uint32_t uu = active ? a.u[p] : 0u, ii = active ? a.i[p] : 0u;
+    const float4 *tp = reinterpret_cast<const float4 *>(a.Et) + (size_t)uu * a.K4;
+    const float4 *bp = reinterpret_cast<const float4 *>(a.Eb) + (size_t)ii * a.K4;
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const uint32_t q = gl + v * G;
+      if (active && q < a.K4) {
+        const float4 t4 = ldg4(tp + q), b4 = ldg4(bp + q);
+        dot = fmaf(t4.x, b4.x, dot);
+        dot = fmaf(t4.y, b4.y, dot);
+        dot = fmaf(t4.z, b4.z, dot);
+        dot = fmaf(t4.w, b4.w, dot);
+      }
+    }
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (active && gl == 0) {
+      double s = (double)dot;
+      if (a.Etb != nullptr) s += (double)a.Etb[uu] + (double)a.Ebb[ii];
+      if (s < 1e-30) s = 1e-30;
+      const uint32_t yy = a.y[p];
+      if (a.binary)
+        local += yy == 0 ? -s : log(1.0 - exp(-s));
+      else
+        local += (double)yy * log(s) - s - a.logfact[yy];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if (lane == 0) wsum[w] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < kSweepThreads / 32; ++q) s += wsum[q];
+    a.block_sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void sum_blocks_kernel(const double *block_sums, uint32_t nblocks, double *out)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (uint32_t b = 0; b < nblocks; ++b) s += block_sums[b];
+    *out = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ratings set-up: CSR -> CSC helpers (the sort itself is cub::DeviceRadixSort)
+// ---------------------------------------------------------------------------
+__global__ void expand_rows_kernel(const uint64_t *row_ptr, uint32_t nrows, uint64_t nnz, uint32_t *row_of)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  uint32_t lo = 0, hi = nrows; // largest r with row_ptr[r] <= j
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+  }
+  row_of[j] = lo;
+}
+
+__global__ void iota_kernel(uint32_t *p, uint64_t n)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) p[j] = (uint32_t)j;
+}
+
+__global__ void gather_csc_kernel(const uint32_t *perm, const uint32_t *row_of, const uint8_t *y, uint64_t nnz,
+                                  uint32_t *csc_row, uint8_t *csc_y)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const uint32_t p = perm[j];
+  csc_row[j] = row_of[p];
+  if (y != nullptr) csc_y[j] = y[p];
+}
+
+// col_ptr[c] = first position whose sorted key is >= c
+__global__ void col_ptr_kernel(const uint32_t *sorted_col, uint64_t nnz, uint32_t ncols, uint64_t *col_ptr)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > nnz) return;
+  const uint32_t prev = j == 0 ? 0u : sorted_col[j - 1] + 1u;
+  const uint32_t cur = j == nnz ? ncols + 1u : sorted_col[j] + 1u;
+  // keys in (prev-1, cur-1] start at j
+  for (uint32_t c = (j == 0 ? 0u : prev); c < cur && c <= ncols; ++c) col_ptr[c] = j;
+}
+
+} // namespace hpf

@@ -1,0 +1,186 @@
+/* hpf_cuda.h -- C ABI of libhpf_b200.so: the B200 (sm_100a) CAVI engine for
+ * (Hierarchical) Poisson Factorization that replaces the hot path of
+ * premgopalan/hgaprec.
+ *
+ * The reference has no plugin / FFI interface: its boundary is
+ * the three loop bodies HGAPRec::vb_hier / vb / vb_bias and the GPMatrix /
+ * GPMatrixGR / GPArray accessors every downstream consumer reads.  This header
+ * is the boundary a maintainer binds instead; INTEGRATION.md shows the stub.
+ * Paths below are relative to the reference tree (/root/reference).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - every host matrix is contiguous row-major fp64 (the reference's
+ *     Matrix = D2Array<double>, src/env.hh:23, flattened row by row).
+ *   - the caller owns all host buffers; the library copies during the call and
+ *     never keeps a host pointer.  The library owns all device memory, its
+ *     stream and its NCCL communicator inside hpf_ctx.
+ *   - return 0 on success, a negative HPF_E* code on failure; the message is
+ *     available from hpf_last_error().  Nothing exits or throws across the ABI
+ *     (the reference exit(-1)s / asserts, e.g. src/hgaprec.cc:42-45); the host
+ *     wrapper maps nonzero to its own lerr()+exit(-1).
+ *   - one host thread per ctx; a ctx is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device hpf_create fails.
+ */
+#ifndef HPF_CUDA_H
+#define HPF_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HPF_API __attribute__((visibility("default")))
+#else
+#define HPF_API
+#endif
+
+/* error codes */
+#define HPF_OK          0
+#define HPF_EINVAL     (-1) /* bad argument / call order                      */
+#define HPF_ECUDA      (-2) /* CUDA runtime error                              */
+#define HPF_ENOMEM     (-3) /* host or device allocation failed                */
+#define HPF_ENCCL      (-4) /* NCCL missing or failed                          */
+#define HPF_ENODEVICE  (-5) /* no usable CUDA device (there is no CPU path)    */
+
+/* hpf_config.flags -- mirror the reference's CLI switches (src/main.cc:99-232) */
+#define HPF_HIER    1u /* -hier        : vb_hier(), src/hgaprec.cc:1321-1436          */
+#define HPF_BIAS    2u /* -bias        : K+2 wide phi, src/hgaprec.cc:222-239         */
+#define HPF_BINARY  4u /* -binary-data : likelihood form, src/hgaprec.cc:1557-1558    */
+#define HPF_JACOBI  8u /* -novb        : vb_bias() else-branch, src/hgaprec.cc:1276-1297
+                          (ignored with HPF_HIER, as in the reference)                */
+
+/* which parameter set a get/set call addresses; names follow HGAPRec's members
+ * (src/hgaprec.hh:105-115).  With HPF_HIER, THETA/BETA are _htheta/_hbeta
+ * (GPMatrix, rate n x k); without, _theta/_beta (GPMatrixGR, rate is a k-vector). */
+enum hpf_param {
+  HPF_THETA = 0,     /* n x k                                   */
+  HPF_BETA = 1,      /* m x k                                   */
+  HPF_THETARATE = 2, /* n     (GPArray _thetarate, hier only)   */
+  HPF_BETARATE = 3,  /* m     (GPArray _betarate,  hier only)   */
+  HPF_THETABIAS = 4, /* n x 1 (GPMatrix _thetabias, bias only)  */
+  HPF_BETABIAS = 5   /* m x 1 (GPMatrix _betabias,  bias only)  */
+};
+
+typedef struct hpf_ctx hpf_ctx;
+
+typedef struct hpf_config {
+  uint32_t abi_version;   /* HPF_ABI_VERSION */
+  uint32_t n_users;       /* users held by THIS ctx (the local shard)              */
+  uint32_t n_items;       /* m: all items (the beta side is replicated per rank)   */
+  uint32_t k;             /* factors                                               */
+  uint32_t flags;         /* HPF_HIER | HPF_BIAS | HPF_BINARY | HPF_JACOBI          */
+  int32_t  device;        /* CUDA device ordinal                                   */
+  uint64_t n_users_global;/* all users over all ranks (0 == n_users); the item-bias
+                             rate adds it, src/hgaprec.cc:1394                      */
+  /* (shape, rate) priors.  The reference hard-codes 0.3 for every one of them
+   * (src/hgaprec.cc:13-20; -a/-b/-c/-d are parsed but never used).             */
+  double theta_shape, theta_rate;         /* _theta / _htheta                    */
+  double beta_shape, beta_rate;           /* _beta / _hbeta                      */
+  double thetarate_shape, thetarate_rate; /* _thetarate (xi)                     */
+  double betarate_shape, betarate_rate;   /* _betarate (eta)                     */
+  double thetabias_shape, thetabias_rate; /* _thetabias                          */
+  double betabias_shape, betabias_rate;   /* _betabias                           */
+} hpf_config;
+
+/* counters readable after any call (all monotone since hpf_create) */
+typedef struct hpf_stats {
+  uint64_t kernel_launches;  /* kernels of this library launched so far            */
+  uint64_t iterations;       /* CAVI iterations completed                          */
+  uint64_t slow_path_nnz;    /* nonzeros that took the exact log-domain fallback   */
+  uint64_t nnz;              /* training nonzeros held                             */
+  uint64_t device_bytes;     /* device memory currently allocated by the ctx       */
+  float    last_iterate_ms;  /* device time of the last hpf_iterate (CUDA events
+                                on the library's own stream)                       */
+  uint32_t sweep_group;      /* lanes cooperating on one nonzero in the sweep      */
+  uint32_t sweep_vec;        /* float4 values per lane                             */
+} hpf_stats;
+
+/* Fill *cfg with the reference's defaults (all priors 0.3, device 0). */
+HPF_API void hpf_config_default(hpf_config *cfg);
+
+HPF_API int hpf_create(const hpf_config *cfg, hpf_ctx **out);
+HPF_API void hpf_destroy(hpf_ctx *ctx);
+
+/* Last error text of this ctx (ctx == NULL: of the last failed hpf_create on
+ * this thread).  Never NULL. */
+HPF_API const char *hpf_last_error(const hpf_ctx *ctx);
+
+/* Training matrix as CSR over the ctx's users, in the order the reference's
+ * loop walks it: row u lists Ratings::get_movies(u) in file order and y holds
+ * Ratings::r(u, i) (src/hgaprec.cc:1340-1345, src/ratings.hh:153-181).
+ * row_ptr: n_users+1 entries; col_idx, y: row_ptr[n_users] entries;
+ * y == NULL means every rating is 1 (-binary-data).  Replaces the Ratings
+ * adjacency-list iterator (src/env.hh:36-37).  May be called again to replace
+ * the matrix. */
+HPF_API int hpf_set_ratings_csr(hpf_ctx *ctx, const uint64_t *row_ptr,
+                        const uint32_t *col_idx, const uint8_t *y);
+
+/* Upload / download one parameter set: shape_curr(), rate_curr(), expected_v(),
+ * expected_logv() of the matching GP* object (src/gpbase.hh:81-93, 463-475,
+ * 807-819).  Host arrays are fp64 row-major (rows x k, or rows for the
+ * GPArray / bias sets; the RATE of THETA/BETA without HPF_HIER is k long).
+ * In hpf_get_state any pointer may be NULL.  hpf_set_state needs all four for
+ * THETA/BETA/THETABIAS/BETABIAS (the reference's initial expectations are NOT
+ * a function of its initial rates, src/gpbase.hh:324-340); THETARATE/BETARATE
+ * need shape, rate and Ev. */
+HPF_API int hpf_set_state(hpf_ctx *ctx, int which, const double *shape, const double *rate,
+                  const double *Ev, const double *Elogv);
+HPF_API int hpf_get_state(hpf_ctx *ctx, int which, double *shape, double *rate,
+                  double *Ev, double *Elogv);
+
+/* THE HOT PATH: n_iters full CAVI iterations (one pass of the loop bodies at
+ * src/hgaprec.cc:1336-1435 / 927-979 / 1226-1318 without the report block).
+ * Returns after the work has completed on the device. */
+HPF_API int hpf_iterate(hpf_ctx *ctx, uint32_t n_iters);
+
+/* compute_likelihood's sum (src/hgaprec.cc:1439-1470, 1503-1570) over held-out
+ * (user, item, y) triples; users are LOCAL row numbers of this ctx.
+ * *sum_ll receives the sum (the reference divides by npairs itself). */
+HPF_API int hpf_heldout_loglik(hpf_ctx *ctx, const uint32_t *u, const uint32_t *i,
+                       const uint8_t *y, uint64_t npairs, double *sum_ll);
+
+/* compute_precision's scoring pass (src/hgaprec.cc:1703-1763, 1969-1991): for
+ * each listed local user score every item with E[theta_u].E[beta_i] (+biases),
+ * force the items of the user's exclusion list (train U validation) to 0.0 --
+ * they stay candidates, as in the reference -- and return the topn best
+ * (descending score, ties by ascending item).  excl_ptr: nu+1 entries.
+ * items_out / scores_out: nu x topn. */
+HPF_API int hpf_topn(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
+             const uint64_t *excl_ptr, const uint32_t *excl_idx, uint32_t topn,
+             uint32_t *items_out, float *scores_out);
+
+/* Multi-GPU (one process per GPU, users sharded, beta replicated): join an NCCL
+ * communicator.  Rank 0 obtains an id with hpf_comm_unique_id and hands it to
+ * the other ranks by any means (bench.py uses torch.distributed).  After this,
+ * hpf_iterate all-reduces the item-side accumulators once per iteration and
+ * hpf_heldout_loglik stays rank-local. */
+#define HPF_COMM_ID_BYTES 128
+HPF_API int hpf_comm_unique_id(void *id_out, size_t id_bytes);
+HPF_API int hpf_comm_init(hpf_ctx *ctx, int rank, int nranks, const void *id, size_t id_bytes);
+
+HPF_API int hpf_get_stats(const hpf_ctx *ctx, hpf_stats *out);
+
+/* Measurement aid: run n_iters iterations with CUDA events recorded on the
+ * library's stream around every kernel class and return the AVERAGE device
+ * time per iteration of each (milliseconds).  Same arithmetic as hpf_iterate. */
+typedef struct hpf_iter_profile {
+  float sweep_user_ms;   /* phi sweep over the CSR (rows = users)              */
+  float sweep_item_ms;   /* phi sweep over the CSC (rows = items)              */
+  float combine_ms;      /* partial-sum combine of split rows (both sides)     */
+  float update_theta_ms; /* dense theta row update + column sums               */
+  float allreduce_ms;    /* NCCL all-reduce of the item-side block (0 if 1 GPU) */
+  float update_beta_ms;  /* dense beta row update + column sums                */
+  float total_ms;        /* first kernel start to last kernel end              */
+} hpf_iter_profile;
+HPF_API int hpf_iterate_profiled(hpf_ctx *ctx, uint32_t n_iters, hpf_iter_profile *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPF_CUDA_H */

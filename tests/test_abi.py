@@ -1,0 +1,65 @@
+"""CPU tests of the drop-in boundary: libhpf_b200.so loads, exports every symbol
+include/hpf_cuda.h declares, and refuses to run without a CUDA device (there is
+no CPU fallback to silently fall into)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import hgaprec_b200 as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hpf_cuda.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"HPF_API\s+[\w\s\*]+?\b(hpf_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("hpf_create", "hpf_destroy", "hpf_set_ratings_csr", "hpf_set_state", "hpf_get_state",
+              "hpf_iterate", "hpf_heldout_loglik", "hpf_topn", "hpf_comm_init", "hpf_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(H.LIB_PATH), "build with __graft_entry__.build()"
+    lib = ctypes.CDLL(H.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), "libhpf_b200.so does not export %s" % s
+
+
+def test_config_struct_layout_matches_header():
+    # the python mirror must have one field per header field, same order
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct hpf_config {"):src.index("} hpf_config;")]
+    names = []
+    for line in body.splitlines()[1:]:
+        line = line.split("/*")[0]
+        m = re.match(r"\s*(uint32_t|int32_t|uint64_t|double)\s+([^;]+);", line)
+        if m:
+            names += [n.strip() for n in m.group(2).split(",")]
+    from hgaprec_b200.capi import _Config
+    assert [f[0] for f in _Config._fields_] == names
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(H.HpfError) as ei:
+        H.Engine(8, 8, 4)
+    assert ei.value.code == -5  # HPF_ENODEVICE
+    assert "no CUDA device" in str(ei.value)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "hgaprec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in txt.replace("hpf_oracle_not", ""), "%s mentions the oracle" % fn

@@ -1,0 +1,226 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through
+the C ABI (hgaprec_b200.Engine -> libhpf_b200.so) and is compared with the fp64
+oracle / the reference's own golden states.  Tolerances: util.TOL_* (SURVEY.md 8c)."""
+import numpy as np
+import pytest
+
+import util
+import hgaprec_b200 as H
+from hgaprec_b200 import synth
+from oracle import hpf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(state, n_users=None, **kw):
+    return H.Engine(state.n if n_users is None else n_users, state.m, state.k, flags=util.engine_flags(state), **kw)
+
+
+def run_engine(state, rp, ci, y, iters):
+    with make_engine(state) as e:
+        e.set_ratings_csr(rp, ci, y)
+        util.push_state(e, state)
+        e.iterate(iters)
+        return util.pull_state(e, state), e.stats()
+
+
+# ------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("mode", util.MODES)
+def test_one_iteration_matches_reference_golden(mode):
+    g = util.load_golden(mode)
+    s0 = util.golden_state(g, 0)
+    got, st = run_engine(s0, g["csr.row_ptr"], g["csr.col_idx"], g["csr.y"], 1)
+    bad = util.compare_states(got, util.golden_state(g, 1))
+    assert not bad, bad
+    assert st["slow_path_nnz"] == 0 and st["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("mode", util.MODES)
+def test_three_iterations_and_heldout_match_reference_golden(mode):
+    g = util.load_golden(mode)
+    s0 = util.golden_state(g, 0)
+    with make_engine(s0) as e:
+        e.set_ratings_csr(g["csr.row_ptr"], g["csr.col_idx"], g["csr.y"])
+        util.push_state(e, s0)
+        # the reference's initial expectations are not a function of its rates:
+        # held-out ll of the uploaded state must reproduce the reference's T=0 number
+        for split in ("validation", "test"):
+            ll0 = e.heldout_loglik(g[split + ".u"], g[split + ".i"], g[split + ".y"])
+            ref0 = float(g["T0/%s.ll_sum" % split][0])
+            assert abs(ll0 - ref0) <= 2e-5 * max(1.0, abs(ref0))
+        e.iterate(3)
+        got = util.pull_state(e, s0)
+        bad = util.compare_states(got, util.golden_state(g, 3), rel=6e-5, elog_abs=6e-5)
+        assert not bad, bad
+        for split in ("validation", "test"):
+            npairs = len(g[split + ".u"])
+            ll = e.heldout_loglik(g[split + ".u"], g[split + ".i"], g[split + ".y"]) / npairs
+            ref = float(g["T3/%s.ll_sum" % split][0]) / npairs
+            assert abs(ll - ref) <= util.TOL_LL_20IT, (split, ll, ref)
+
+
+# --------------------------------------------------- oracle at config shapes
+def _oracle_case(n, m, nnz, k, flags, seed, binary=False):
+    d = synth.make_ratings(n, m, nnz, binary=binary, seed=seed, heldout=0.05)
+    s = O.OracleState(d["n"], d["m"], k, flags).init(seed + 1)
+    return d, s
+
+
+@pytest.mark.parametrize("name,n,m,nnz,k,flags,binary", [
+    ("C1-shape hier K=100", 6040, 3681, 792166, 100, H.HIER, False),
+    ("C3-shape hier binary K=200", 5000, 1900, 240000, 200, H.HIER | H.BINARY, True),
+    ("C4-shape bpf bias K=100", 8000, 800, 400000, 100, H.BIAS, False),
+    ("hier bias K=100", 3000, 1500, 200000, 100, H.HIER | H.BIAS, False),
+])
+def test_single_iteration_matches_oracle(name, n, m, nnz, k, flags, binary):
+    d, s = _oracle_case(n, m, nnz, k, flags, seed=11, binary=binary)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 1, nthreads=8)
+    got, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 1)
+    bad = util.compare_states(got, want)
+    assert not bad, (name, bad)
+    assert st["slow_path_nnz"] == 0
+
+
+def test_twenty_iterations_movielens_shape_trajectory():
+    """C1-sized problem, K=100, -hier: 20 iterations against the fp64 oracle."""
+    d, s = _oracle_case(6040, 3681, 792166, 100, H.HIER, seed=111)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 20, nthreads=8)
+    hu, hi, hy = d["heldout"]
+    with make_engine(s) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(20)
+        got = util.pull_state(e, s)
+        ll = e.heldout_loglik(hu, hi, hy) / len(hu)
+    ref = want.heldout(hu, hi, hy) / len(hu)
+    assert abs(ll - ref) <= util.TOL_LL_20IT, (ll, ref)
+    for gname in ("theta", "beta"):
+        rf = util.rel_fro(got.p[gname]["Ev"], want.p[gname]["Ev"])
+        assert rf <= util.TOL_RELFRO_20IT, (gname, rf)
+        rel = np.abs(got.p[gname]["Ev"] - want.p[gname]["Ev"]) / np.maximum(np.abs(want.p[gname]["Ev"]), 1e-3)
+        assert np.percentile(rel, 99) <= 5e-4
+
+
+# ---------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("k", [1, 3, 5, 33, 100, 130, 257])
+def test_ragged_k(k):
+    d, s = _oracle_case(300, 120, 6000, k, H.HIER, seed=5 + k)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 2)
+    got, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 2)
+    bad = util.compare_states(got, want, rel=4e-5, elog_abs=4e-5)
+    assert not bad, bad
+
+
+def test_empty_rows_long_rows_duplicates_and_big_ratings():
+    rng = np.random.default_rng(3)
+    n, m, k = 400, 700, 20
+    rows = []
+    for u in range(n):
+        if u in (0, 17, 399):
+            rows.append(np.zeros(0, dtype=np.uint32))            # users without ratings
+        elif u == 5:
+            rows.append(rng.permutation(600).astype(np.uint32))  # > seg_len: split user row
+        else:
+            others = 1 + rng.choice(599, size=rng.integers(1, 30), replace=False)
+            rows.append(np.concatenate([[0], others]).astype(np.uint32))  # item 0: > seg_len users -> split item row
+    rows[7] = np.array([3, 9, 3, 3], dtype=np.uint32)            # duplicate (u,i): processed once per entry
+    ci = np.concatenate(rows)                                    # items 600..699 have no ratings
+    rp = np.zeros(n + 1, dtype=np.uint64)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    y = rng.integers(1, 6, size=len(ci)).astype(np.uint8)
+    y[::7] = 255                                                 # yval_t is uint8 (env.hh:20)
+    s = O.OracleState(n, m, k, H.HIER | H.BIAS).init(9)
+    want = s.copy().iterate(rp, ci, y, 2)
+    got, _ = run_engine(s, rp, ci, y, 2)
+    bad = util.compare_states(got, want, rel=4e-5, elog_abs=4e-5)
+    assert not bad, bad
+
+
+def test_no_ratings_at_all_and_y_null():
+    n, m, k = 10, 12, 4
+    s = O.OracleState(n, m, k, 0).init(2)
+    rp = np.zeros(n + 1, dtype=np.uint64)
+    want = s.copy().iterate(rp, np.zeros(0, np.uint32), None, 1)
+    got, _ = run_engine(s, rp, np.zeros(0, np.uint32), None, 1)
+    assert not util.compare_states(got, want)
+    d, s = _oracle_case(200, 90, 3000, 10, H.HIER | H.BINARY, seed=4, binary=True)
+    assert d["y"] is None
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], None, 1)
+    got, _ = run_engine(s, d["row_ptr"], d["col_idx"], None, 1)
+    assert not util.compare_states(got, want)
+
+
+def test_exact_fallback_when_products_underflow():
+    """Rows whose log-expectations peak in different factors by > 100 nats make
+    the fp32 product form underflow; the engine must take the log-domain path
+    and still match the oracle."""
+    d, s = _oracle_case(64, 48, 900, 8, H.HIER, seed=21)
+    el_t, el_b = s.p["theta"]["Elogv"], s.p["beta"]["Elogv"]
+    el_t[:, :] = -120.0
+    el_t[:, 0] = 0.0          # theta rows peak at k=0
+    el_b[:, :] = -130.0
+    el_b[:, 5] = 1.0          # beta rows peak at k=5
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 1)
+    got, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 1)
+    assert st["slow_path_nnz"] == 2 * len(d["col_idx"])  # both passes
+    bad = util.compare_states(got, want, rel=4e-5, elog_abs=4e-5)
+    assert not bad, bad
+    # and the next iteration (ordinary state again) runs on the fast path
+    want.iterate(d["row_ptr"], d["col_idx"], d["y"], 1)
+    with make_engine(s) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(2)
+        got2 = util.pull_state(e, s)
+        assert e.stats()["slow_path_nnz"] == 2 * len(d["col_idx"])
+    assert not util.compare_states(got2, want, rel=6e-5, elog_abs=6e-5)
+
+
+def test_runs_are_bitwise_deterministic():
+    d, s = _oracle_case(2000, 700, 90000, 100, H.HIER | H.BIAS, seed=8)
+    a, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    b, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    for gname in util.groups(a):
+        for f in O.FIELDS:
+            np.testing.assert_array_equal(a.p[gname][f], b.p[gname][f])
+
+
+def test_errors_are_reported_not_fatal():
+    with H.Engine(4, 4, 3) as e:
+        with pytest.raises(H.HpfError):
+            e.iterate(1)  # nothing set yet
+        rp = np.array([0, 1, 2, 2, 3], dtype=np.uint64)
+        with pytest.raises(H.HpfError):
+            e.set_ratings_csr(rp, np.array([0, 9, 1], dtype=np.uint32))  # item 9 >= m
+    with pytest.raises(H.HpfError):
+        H.Engine(4, 4, 0)
+
+
+# ----------------------------------- size-independent property at full size
+def test_full_size_netflix_shape_mass_conservation():
+    """BASELINE config C2 (480,189 x 17,770, 1e8 nnz, K=100, -hier): phi sums to
+    one per nonzero, so for every user sum_k (shape_uk - prior) == sum_i y_ui
+    and likewise per item (hgaprec.cc:1355-1359).  Checked on every row."""
+    c = synth.CONFIGS["netflix"]
+    d = synth.make_ratings(c["n"], c["m"], c["nnz"], seed=c["seed"])
+    n, m, k = d["n"], d["m"], 100
+    rng = np.random.default_rng(0)
+    with H.Engine(n, m, k, flags=H.HIER) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        for which, rows in ((H.THETA, n), (H.BETA, m)):
+            shp = 0.3 + 0.01 * rng.random((rows, k))
+            rate = 0.3 + 0.1 * rng.random((rows, k))
+            e.set_state(which, shp, rate, shp / rate, np.log(shp / rate) - 0.5 / shp)
+        for which, rows in ((H.THETARATE, n), (H.BETARATE, m)):
+            e.set_state(which, np.full(rows, 0.3), np.full(rows, 100.3), np.full(rows, 0.3 / 100.3))
+        e.iterate(2)
+        th = e.get_state(H.THETA, fields=("shape",))["shape"]
+        be = e.get_state(H.BETA, fields=("shape",))["shape"]
+        assert e.stats()["slow_path_nnz"] == 0
+    rp = d["row_ptr"].astype(np.int64)
+    ysum_u = np.add.reduceat(np.concatenate([d["y"].astype(np.float64), [0.0]]), rp[:-1])[:n]
+    ysum_u[rp[1:] == rp[:-1]] = 0.0
+    ysum_i = np.bincount(d["col_idx"], weights=d["y"].astype(np.float64), minlength=m)
+    np.testing.assert_allclose((th - 0.3).sum(1), ysum_u, rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose((be - 0.3).sum(1), ysum_i, rtol=2e-5, atol=1e-3)
+    assert np.isfinite(th).all() and np.isfinite(be).all()
