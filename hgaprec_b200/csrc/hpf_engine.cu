@@ -3,14 +3,18 @@
 // hpf_kernels.cuh on the ctx's own stream; there is no CPU compute path.
 //
 // HBM layout per parameter side (theta: R = local users, beta: R = items), all
-// fp32, row stride Kp = K rounded up to 4 floats (16-byte rows for 128-bit loads):
-//   A      [R x Kp]  exp(Elog - rowmax)      sweep input (gathered by the other side)
-//   Elog   [R x Kp]  expected log            fallback path + hpf_get_state
-//   Ev     [R x Kp]  expectation             rate sums, held-out ll, top-N
-//   shape  [R x Kp]  Gamma shape             hpf_get_state / checkpoints
-//   rate   [R x Kp] (hier) or [Kp]           hpf_get_state / checkpoints
-//   T      [R x Kp]  sweep output sum (y/Z) * A_other   (+ Tpart for split rows)
-//   Tdirect[R x Kp]  exact-fallback accumulator (all zero in normal operation)
+// fp32.  Kp = K rounded up to 4 floats (whole float4s hold data; the pad lanes
+// hold 0 / -inf); the row stride ld is Kp rounded up so that a row never
+// straddles more 128-byte lines than it must (a multiple of 32 floats once
+// Kp >= 32, the next power of two below that) -- the gather of one K=100 row
+// then costs 4 L1 wavefronts instead of 7:
+//   A      [R x ld]  exp(Elog - rowmax)      sweep input (gathered by the other side)
+//   Elog   [R x ld]  expected log            fallback path + hpf_get_state
+//   Ev     [R x ld]  expectation             rate sums, held-out ll, top-N
+//   shape  [R x ld]  Gamma shape             hpf_get_state / checkpoints
+//   rate   [R x ld] (hier) or [Kp]           hpf_get_state / checkpoints
+//   T      [R x ld]  sweep output sum (y/Z) * A_other   (+ Tpart for split rows)
+//   Tdirect[R x ld]  exact-fallback accumulator (all zero in normal operation)
 // plus per-row vectors (shift, xi/eta GPArray, bias GPMatrix, aux) and the
 // ratings in both orientations (CSR for the user pass, CSC for the item pass).
 #include "../../include/hpf_cuda.h"
@@ -99,7 +103,7 @@ struct Side {
 
 struct hpf_ctx {
   hpf_config cfg;
-  uint32_t K = 0, Kp = 0, K4 = 0;
+  uint32_t K = 0, Kp = 0, K4 = 0, ld = 0;
   bool hier = false, bias = false, binary = false, jacobi = false;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
@@ -107,14 +111,17 @@ struct hpf_ctx {
   cudaEvent_t pev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   bool profiling = false;
   std::string err;
-  std::vector<void *> allocs;
+  std::vector<std::pair<void *, size_t>> allocs;
   uint64_t device_bytes = 0;
   Side th, be; // theta (users), beta (items)
   // ratings
   uint64_t nnz = 0;
-  uint32_t *csr_idx = nullptr, *csc_idx = nullptr;
-  uint8_t *csr_y = nullptr, *csc_y = nullptr;
-  uint32_t seg_len = 256;
+  uint32_t *csr_idx = nullptr, *csc_idx = nullptr, *upass_idx = nullptr; // upass_*: CSR regrouped by item tile (or null)
+  uint8_t *csr_y = nullptr, *csc_y = nullptr, *upass_y = nullptr;
+  uint32_t th_tiles = 1, be_tiles = 1;
+  uint64_t l2_tile_bytes = 32ull << 20; // factor rows of one gather tile (0: no tiling)
+  uint32_t *scratch_u32 = nullptr;
+  uint32_t seg_len = 512;
   int sweep_g = 0, sweep_v = 0;
   bool aux_dirty = true, ratings_set = false, th_colsum_global = false;
   // item-side reduce block [T_beta | Tb_beta | colsum_theta] (one allreduce)
@@ -158,7 +165,7 @@ template <class T> int dalloc(hpf_ctx *c, T **p, size_t count, bool zero = true)
   if (count == 0) count = 1;
   void *q = nullptr;
   CU(cudaMalloc(&q, count * sizeof(T)));
-  c->allocs.push_back(q);
+  c->allocs.emplace_back(q, count * sizeof(T));
   c->device_bytes += count * sizeof(T);
   if (zero) CU(cudaMemsetAsync(q, 0, count * sizeof(T), c->stream));
   *p = (T *)q;
@@ -168,8 +175,12 @@ template <class T> int dalloc(hpf_ctx *c, T **p, size_t count, bool zero = true)
 int dfree(hpf_ctx *c, void *p)
 {
   if (!p) return 0;
-  auto it = std::find(c->allocs.begin(), c->allocs.end(), p);
-  if (it != c->allocs.end()) c->allocs.erase(it);
+  for (auto it = c->allocs.begin(); it != c->allocs.end(); ++it)
+    if (it->first == p) {
+      c->device_bytes -= it->second;
+      c->allocs.erase(it);
+      break;
+    }
   cudaFree(p);
   return 0;
 }
@@ -187,11 +198,12 @@ uint32_t row_grid(const hpf_ctx *c, uint32_t R)
   return std::max(1u, std::min(need, cap));
 }
 
-// pick lanes-per-nonzero G and float4-per-lane V: smallest G with V <= 7
+// pick lanes-per-nonzero G and float4-per-lane V: smallest G with V <= 4 (measured best at K=100:
+// G=8/V=4 beats G=4/V=7 -- fewer registers, twice the resident warps)
 void pick_sweep_shape(hpf_ctx *c)
 {
   int g = 1;
-  while (g < 32 && (int)((c->K4 + g - 1) / g) > 7) g *= 2;
+  while (g < 32 && (int)((c->K4 + g - 1) / g) > 4) g *= 2;
   if (const char *e = getenv("HPF_SWEEP_G")) {
     int eg = atoi(e);
     if (eg == 1 || eg == 2 || eg == 4 || eg == 8 || eg == 16 || eg == 32)
@@ -204,7 +216,7 @@ void pick_sweep_shape(hpf_ctx *c)
 int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
 {
   s.R = R;
-  const size_t rk = (size_t)R * c->Kp;
+  const size_t rk = (size_t)R * c->ld;
   TRY(dalloc(c, &s.A, rk));
   TRY(dalloc(c, &s.Elog, rk));
   TRY(dalloc(c, &s.Ev, rk));
@@ -274,7 +286,7 @@ int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside)
   a.ElogbRow = rowside.b_Elog; a.ElogbCol = colside.b_Elog;
   a.Tdirect = rowside.Tdirect; a.Tbdirect = rowside.Tbdirect;
   a.direct_flag = rowside.direct_flag; a.slow_count = c->slow_count;
-  a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4;
+  a.K = c->K; a.K4 = c->K4; a.ld = c->ld; a.ld4 = c->ld / 4;
   switch (c->sweep_g) {
   case 1: return launch_sweep_g<1>(c, a);
   case 2: return launch_sweep_g<2>(c, a);
@@ -291,7 +303,7 @@ int launch_combine(hpf_ctx *c, Side &s)
   if (s.wl.nmulti == 0) return 0;
   CombineArgs a;
   a.multi_row = s.wl.multi_row; a.multi_first = s.wl.multi_first; a.multi_cnt = s.wl.multi_cnt;
-  a.nmulti = s.wl.nmulti; a.Kp = c->Kp; a.Tpart = s.Tpart; a.T = s.T;
+  a.nmulti = s.wl.nmulti; a.Kp = c->Kp; a.ld = c->ld; a.Tpart = s.Tpart; a.T = s.T;
   a.Tbpart = c->bias ? s.Tbpart : nullptr; a.Tb = s.Tb;
   const size_t sm = ((size_t)kUpdateWarps * c->Kp + kUpdateWarps) * sizeof(float);
   combine_kernel<<<s.wl.nmulti, kUpdateWarps * 32, sm, c->stream>>>(a);
@@ -304,7 +316,7 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
 {
   UpdateArgs a;
   memset(&a, 0, sizeof a);
-  a.R = s.R; a.K = c->K; a.Kp = c->Kp;
+  a.R = s.R; a.K = c->K; a.Kp = c->Kp; a.ld = c->ld;
   a.T = s.T; a.Tdirect = s.Tdirect; a.direct_flag = s.direct_flag;
   a.A = s.A; a.Elog = s.Elog; a.Ev = s.Ev; a.shape = s.shape; a.rate = s.rate; a.shift = s.shift;
   a.hier = c->hier; a.colsum_other = colsum_other;
@@ -330,7 +342,7 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
 int refresh_colsum(hpf_ctx *c, Side &s)
 {
   const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
-  colsum_partial_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(s.Ev, s.R, c->Kp, s.colsum_partial);
+  colsum_partial_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(s.Ev, s.R, c->Kp, c->ld, s.colsum_partial);
   c->launches++;
   CU(cudaGetLastError());
   colsum_finalize_kernel<<<(c->Kp + 127) / 128, 128, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
@@ -341,58 +353,82 @@ int refresh_colsum(hpf_ctx *c, Side &s)
 }
 
 // ---- work lists ---------------------------------------------------------------
-// Split every row into segments of <= seg_len nonzeros; a row with one segment
-// writes its T row directly, a row with several writes partial slots that
-// combine_kernel adds in order.  Segments are counting-sorted by descending
-// length so that (a) the 32/G segments a warp advances in lock-step have equal
-// trip counts and (b) long work is scheduled first.
-int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, const uint32_t *d_idx, const uint8_t *d_y)
+// The nonzeros of one orientation arrive as RUNS: run (t, r) holds the nonzeros
+// of row r whose gathered-side index lies in tile t, ptr[t * R + r] is where it
+// starts (ntiles == 1: ptr is the plain CSR row pointer).  Every run is split
+// into segments of <= seg_len nonzeros.  A row with one segment writes its T row
+// directly; a row with several writes partial slots that combine_kernel adds in
+// a fixed order.  Segments are emitted tile by tile -- blocks are scheduled in
+// index order, so at any moment the gathers fall into one tile's L2-resident
+// factor rows -- and, inside a tile, counting-sorted by descending length so
+// that (a) the 32/G segments a warp advances in lock-step have equal trip counts
+// and (b) long work is scheduled first.
+int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, uint32_t ntiles, const uint32_t *d_idx, const uint8_t *d_y)
 {
   WorkList &w = s.wl;
   dfree(c, w.seg); dfree(c, w.seg_out); dfree(c, w.multi_row); dfree(c, w.multi_first); dfree(c, w.multi_cnt);
   w = WorkList();
   w.idx = d_idx; w.y = d_y;
   const uint32_t R = s.R, L = c->seg_len;
-  uint64_t nsegs64 = 0;
-  for (uint32_t r = 0; r < R; ++r) {
-    const uint64_t len = ptr[r + 1] - ptr[r];
-    nsegs64 += len == 0 ? 1 : (len + L - 1) / L;
+  std::vector<uint32_t> segcnt(R, 0);
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    const uint64_t *pt = ptr + (size_t)t * R;
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint64_t len = pt[r + 1] - pt[r];
+      if (len) segcnt[r] += (uint32_t)((len + L - 1) / L);
+    }
   }
+  uint64_t nsegs64 = 0;
+  for (uint32_t r = 0; r < R; ++r) nsegs64 += segcnt[r] ? segcnt[r] : 1;
   if (nsegs64 >= 0xfffffff0ull) return fail(c, HPF_EINVAL, "too many work segments (%llu)", (unsigned long long)nsegs64);
   const uint32_t nsegs = (uint32_t)nsegs64;
+  std::vector<uint32_t> multi_row, multi_first, multi_cnt, first(R, 0), next(R, 0);
+  uint32_t nslots = 0;
+  for (uint32_t r = 0; r < R; ++r)
+    if (segcnt[r] > 1) {
+      multi_row.push_back(r); multi_first.push_back(nslots); multi_cnt.push_back(segcnt[r]);
+      first[r] = nslots;
+      nslots += segcnt[r];
+    }
   std::vector<uint4> seg(nsegs);
   std::vector<uint32_t> seg_out(nsegs);
-  std::vector<uint32_t> multi_row, multi_first, multi_cnt;
-  // counting sort by length, descending: bucket b holds length L - b
-  std::vector<uint32_t> bucket(L + 2, 0);
-  for (uint32_t r = 0; r < R; ++r) {
-    const uint64_t len = ptr[r + 1] - ptr[r];
-    if (len <= L) bucket[L - (uint32_t)len + 1]++;
-    else {
+  std::vector<uint32_t> bucket(L + 2);
+  uint32_t base = 0;
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    const uint64_t *pt = ptr + (size_t)t * R;
+    // counting sort by length, descending: bucket b holds length L - b
+    std::fill(bucket.begin(), bucket.end(), 0u);
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint64_t len = pt[r + 1] - pt[r];
+      if (len == 0) {
+        if (t == 0 && segcnt[r] == 0) bucket[L + 1]++; // a row without nonzeros still clears its T row
+        continue;
+      }
       bucket[1] += (uint32_t)(len / L);
       if (len % L) bucket[L - (uint32_t)(len % L) + 1]++;
     }
-  }
-  for (uint32_t b = 1; b < L + 2; ++b) bucket[b] += bucket[b - 1];
-  uint32_t nslots = 0;
-  for (uint32_t r = 0; r < R; ++r) {
-    const uint64_t b0 = ptr[r], len = ptr[r + 1] - ptr[r];
-    if (len <= L) {
-      const uint32_t pos = bucket[L - (uint32_t)len]++;
-      seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, (uint32_t)len);
-      seg_out[pos] = r;
-    } else {
+    for (uint32_t b = 1; b < L + 2; ++b) bucket[b] += bucket[b - 1];
+    const uint32_t tile_segs = bucket[L + 1];
+    for (uint32_t r = 0; r < R; ++r) {
+      const uint64_t b0 = pt[r], len = pt[r + 1] - pt[r];
+      if (len == 0) {
+        if (t == 0 && segcnt[r] == 0) {
+          const uint32_t pos = base + bucket[L]++;
+          seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, 0u);
+          seg_out[pos] = r;
+        }
+        continue;
+      }
       const uint32_t cnt = (uint32_t)((len + L - 1) / L);
-      multi_row.push_back(r); multi_first.push_back(nslots); multi_cnt.push_back(cnt);
       for (uint32_t q = 0; q < cnt; ++q) {
         const uint64_t sb = b0 + (uint64_t)q * L;
         const uint32_t sl = (uint32_t)std::min<uint64_t>(L, len - (uint64_t)q * L);
-        const uint32_t pos = bucket[L - sl]++;
+        const uint32_t pos = base + bucket[L - sl]++;
         seg[pos] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
-        seg_out[pos] = R + nslots + q;
+        seg_out[pos] = segcnt[r] == 1 ? r : R + first[r] + next[r]++;
       }
-      nslots += cnt;
     }
+    base += tile_segs;
   }
   w.nsegs = nsegs; w.npartial = nslots; w.nmulti = (uint32_t)multi_row.size();
   TRY(dalloc(c, &w.seg, nsegs, false));
@@ -409,12 +445,98 @@ int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, const uint32_t *d_i
   }
   if (nslots > s.part_rows_cap) {
     dfree(c, s.Tpart); dfree(c, s.Tbpart);
-    TRY(dalloc(c, &s.Tpart, (size_t)nslots * c->Kp, false));
+    s.Tpart = nullptr; s.Tbpart = nullptr;
+    TRY(dalloc(c, &s.Tpart, (size_t)nslots * c->ld, false));
     if (c->bias) TRY(dalloc(c, &s.Tbpart, nslots, false));
     s.part_rows_cap = nslots;
   }
   CU(cudaStreamSynchronize(c->stream)); // host vectors go out of scope
   return 0;
+}
+
+// scratch device memory of one set-up call
+struct Scratch {
+  std::vector<void *> v;
+  ~Scratch() { for (void *p : v) cudaFree(p); }
+  template <class T> cudaError_t get(T **p, size_t count)
+  {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
+    if (e == cudaSuccess) v.push_back(q);
+    *p = (T *)q;
+    return e;
+  }
+};
+
+int bits_for(uint64_t nvalues)
+{
+  int b = 1;
+  while (b < 32 && (1ull << b) < nvalues) ++b;
+  return b;
+}
+
+// how many tiles the gathered side (C rows of ld floats) is cut into
+uint32_t tiles_for(const hpf_ctx *c, uint32_t C, uint32_t R)
+{
+  if (c->l2_tile_bytes == 0) return 1;
+  const uint64_t bytes = (uint64_t)C * c->ld * sizeof(float);
+  if (bytes <= 2 * c->l2_tile_bytes) return 1;
+  uint64_t t = (bytes + c->l2_tile_bytes - 1) / c->l2_tile_bytes;
+  while (t > 1 && t * (uint64_t)R >= 0xfffffff0ull) --t; // the composite key is 32 bits
+  return (uint32_t)std::min<uint64_t>(t, C);
+}
+
+// One orientation of the ratings: nonzeros ordered by (tile of col, row), with
+// the gathered-side index and the rating permuted accordingly, and its work
+// list.  d_row / d_col / d_y are per nonzero in the caller's CSR order.
+// presorted: the input is already ordered by row (the CSR itself).
+int build_orientation(hpf_ctx *c, Side &s, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y, bool presorted,
+                      uint32_t R, uint32_t C, const uint64_t *host_row_ptr, uint32_t **own_idx, uint8_t **own_y,
+                      uint32_t *ntiles_out)
+{
+  const uint64_t nnz = c->nnz;
+  const uint32_t ntiles = tiles_for(c, C, R);
+  const uint32_t tile_cols = (uint32_t)(((uint64_t)C + ntiles - 1) / ntiles);
+  *ntiles_out = ntiles;
+  dfree(c, *own_idx); dfree(c, *own_y);
+  *own_idx = nullptr; *own_y = nullptr;
+  if (presorted && ntiles == 1) return build_worklist(c, s, host_row_ptr, 1, d_col, d_y);
+  std::vector<uint64_t> run_ptr((size_t)ntiles * R + 1, 0);
+  if (nnz > 0) {
+    TRY(dalloc(c, own_idx, nnz, false));
+    if (d_y) TRY(dalloc(c, own_y, nnz, false));
+    Scratch tmp;
+    uint32_t *perm = nullptr, *perm2 = nullptr, *key = nullptr, *key2 = nullptr;
+    uint64_t *d_run = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nnz, 0, 32, c->stream);
+    CU(tmp.get(&perm, nnz)); CU(tmp.get(&perm2, nnz)); CU(tmp.get(&key, nnz)); CU(tmp.get(&key2, nnz));
+    CU(tmp.get(&d_run, run_ptr.size())); CU(tmp.get((char **)&d_tmp, tmp_bytes));
+    const unsigned nb = (unsigned)((nnz + 255) / 256);
+    iota_kernel<<<nb, 256, 0, c->stream>>>(perm, nnz);
+    c->launches++;
+    if (!presorted) { // stable sort by row
+      CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_row, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0,
+                                         bits_for(R), c->stream));
+      std::swap(perm, perm2);
+    }
+    if (ntiles > 1) { // then stable sort by the tile of the gathered-side index
+      gather_key_kernel<<<nb, 256, 0, c->stream>>>(perm, d_col, tile_cols, nnz, key);
+      c->launches++;
+      CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint32_t *)perm, perm2,
+                                         (int64_t)nnz, 0, bits_for(ntiles), c->stream));
+      std::swap(perm, perm2);
+    }
+    apply_perm_kernel<<<nb, 256, 0, c->stream>>>(perm, d_row, d_col, d_y, tile_cols, R, nnz, *own_idx, *own_y, key);
+    run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key, nnz, ntiles * R, d_run);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(run_ptr.data(), d_run, run_ptr.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return build_worklist(c, s, run_ptr.data(), ntiles, *own_idx, *own_y);
 }
 
 int ensure_aux(hpf_ctx *c)
@@ -524,10 +646,14 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   hpf_ctx *n = new hpf_ctx();
   n->cfg = *cfg;
   n->K = cfg->k; n->Kp = (cfg->k + 3u) & ~3u; n->K4 = n->Kp / 4;
+  if (n->Kp >= 32) n->ld = (n->Kp + 31u) & ~31u;
+  else for (n->ld = 4; n->ld < n->Kp; n->ld *= 2) {}
   n->hier = cfg->flags & HPF_HIER; n->bias = cfg->flags & HPF_BIAS; n->binary = cfg->flags & HPF_BINARY;
   n->jacobi = (cfg->flags & HPF_JACOBI) && !n->hier;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   if (const char *e = getenv("HPF_SEG_LEN")) { int v = atoi(e); if (v >= 8 && v <= 65536) n->seg_len = v; }
+  if (const char *e = getenv("HPF_L2_TILE_MB")) { int v = atoi(e); if (v >= 0 && v <= 4096) n->l2_tile_bytes = (uint64_t)v << 20; }
+  if (const char *e = getenv("HPF_L2_TILE_KB")) { int v = atoi(e); if (v >= 0) n->l2_tile_bytes = (uint64_t)v << 10; } // tests
   pick_sweep_shape(n);
   c = n;
   int rc = 0;
@@ -543,18 +669,19 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     c->be.bias_prior_shape = cfg->betabias_shape; c->be.bias_prior_rate = cfg->betabias_rate;
     if ((rc = alloc_side(c, c->th, cfg->n_users))) break;
     if ((rc = alloc_side(c, c->be, cfg->n_items))) break;
-    // item-side reduce block: [T_beta (m x Kp) | Tb_beta (m, padded to 4) | colsum_theta (Kp)]
-    const size_t mk = (size_t)cfg->n_items * c->Kp, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
+    // item-side reduce block: [T_beta (m x ld) | Tb_beta (m, padded to 4) | colsum_theta (Kp)]
+    const size_t mk = (size_t)cfg->n_items * c->ld, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
     c->red_count = mk + mpad + c->Kp;
     if ((rc = dalloc(c, &c->redblock, c->red_count))) break;
     c->be.T = c->redblock;
     c->be.Tb = c->bias ? c->redblock + mk : nullptr;
     c->th.colsum = c->redblock + mk + mpad;
     if ((rc = dalloc(c, &c->be.colsum, c->Kp))) break;
-    if ((rc = dalloc(c, &c->th.T, (size_t)cfg->n_users * c->Kp))) break;
+    if ((rc = dalloc(c, &c->th.T, (size_t)cfg->n_users * c->ld))) break;
     if (c->bias && (rc = dalloc(c, &c->th.Tb, cfg->n_users))) break;
     if ((rc = dalloc(c, &c->colsum_theta_old, c->Kp))) break;
     if ((rc = dalloc(c, &c->slow_count, 1))) break;
+    if ((rc = dalloc(c, &c->scratch_u32, 4))) break;
     if ((rc = dalloc(c, &c->logfact, 256))) break;
     if ((rc = dalloc(c, &c->ll_blocks, (size_t)c->sm_count * 8))) break;
     if ((rc = dalloc(c, &c->ll_out, 1))) break;
@@ -579,7 +706,7 @@ void hpf_destroy(hpf_ctx *c)
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (void *p : c->allocs) cudaFree(p);
+  for (auto &p : c->allocs) cudaFree(p.first);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (auto &e : c->pev) if (e) cudaEventDestroy(e);
@@ -598,49 +725,37 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     if (row_ptr[r + 1] < row_ptr[r]) return fail(c, HPF_EINVAL, "row_ptr not monotone at row %u", r);
   if (nnz > 0 && !col_idx) return fail(c, HPF_EINVAL, "col_idx is null");
   if (nnz >= 0xffffffffull) return fail(c, HPF_EINVAL, "nnz=%llu per ctx exceeds 2^32-1", (unsigned long long)nnz);
-  for (uint64_t j = 0; j < nnz; ++j)
-    if (col_idx[j] >= m) return fail(c, HPF_EINVAL, "col_idx[%llu]=%u >= n_items=%u", (unsigned long long)j, col_idx[j], m);
-  dfree(c, c->csr_idx); dfree(c, c->csc_idx); dfree(c, c->csr_y); dfree(c, c->csc_y);
-  c->csr_idx = c->csc_idx = nullptr; c->csr_y = c->csc_y = nullptr;
+  c->ratings_set = false;
+  dfree(c, c->csr_idx); dfree(c, c->csr_y);
+  c->csr_idx = nullptr; c->csr_y = nullptr;
   c->nnz = nnz;
   TRY(dalloc(c, &c->csr_idx, nnz, false));
-  TRY(dalloc(c, &c->csc_idx, nnz, false));
-  if (y) { TRY(dalloc(c, &c->csr_y, nnz, false)); TRY(dalloc(c, &c->csc_y, nnz, false)); }
-  std::vector<uint64_t> col_ptr(m + 1, 0);
+  if (y) TRY(dalloc(c, &c->csr_y, nnz, false));
+  Scratch tmp;
+  uint64_t *d_rowptr = nullptr;
+  uint32_t *d_rowof = nullptr;
   if (nnz > 0) {
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
-    // CSC by a stable radix sort of (item, position): rows stay ascending per item
-    uint64_t *d_rowptr = nullptr, *d_colptr = nullptr;
-    uint32_t *d_rowof = nullptr, *d_pos = nullptr, *d_pos2 = nullptr, *d_key2 = nullptr;
-    void *d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    int end_bit = 1;
-    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)m) ++end_bit;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nnz, 0, end_bit, c->stream);
-    cudaError_t e = cudaSuccess;
-    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
-    A((void **)&d_rowptr, (n + 1) * 8); A((void **)&d_colptr, ((size_t)m + 1) * 8); A((void **)&d_rowof, nnz * 4);
-    A((void **)&d_pos, nnz * 4); A((void **)&d_pos2, nnz * 4); A((void **)&d_key2, nnz * 4); A(&d_tmp, tmp_bytes);
+    CU(tmp.get(&d_rowptr, (size_t)n + 1)); CU(tmp.get(&d_rowof, nnz));
+    CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     const unsigned nb = (unsigned)((nnz + 255) / 256);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rowptr, row_ptr, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-      expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
-      iota_kernel<<<nb, 256, 0, c->stream>>>(d_pos, nnz);
-      e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)c->csr_idx, d_key2, (const uint32_t *)d_pos,
-                                          d_pos2, (int64_t)nnz, 0, end_bit, c->stream);
-      gather_csc_kernel<<<nb, 256, 0, c->stream>>>(d_pos2, d_rowof, c->csr_y, nnz, c->csc_idx, c->csc_y);
-      col_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(d_key2, nnz, m, d_colptr);
-      c->launches += 4;
-      if (e == cudaSuccess) e = cudaMemcpyAsync(col_ptr.data(), d_colptr, ((size_t)m + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    }
-    cudaFree(d_rowptr); cudaFree(d_colptr); cudaFree(d_rowof); cudaFree(d_pos); cudaFree(d_pos2); cudaFree(d_key2); cudaFree(d_tmp);
-    if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? HPF_ENOMEM : HPF_ECUDA, "CSC build: %s", cudaGetErrorString(e));
+    // argument check on the device: every item index must be < n_items
+    CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
+    check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32);
+    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
+    c->launches += 2;
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", bad, m);
   }
-  TRY(build_worklist(c, c->th, row_ptr, c->csr_idx, c->csr_y));
-  TRY(build_worklist(c, c->be, col_ptr.data(), c->csc_idx, c->csc_y));
+  // user pass: rows = users (the CSR order itself), gathers item rows
+  TRY(build_orientation(c, c->th, d_rowof, c->csr_idx, c->csr_y, true, n, m, row_ptr, &c->upass_idx, &c->upass_y,
+                        &c->th_tiles));
+  // item pass: rows = items, gathers user rows; users stay ascending inside a run
+  TRY(build_orientation(c, c->be, c->csr_idx, d_rowof, c->csr_y, false, m, n, nullptr, &c->csc_idx, &c->csc_y,
+                        &c->be_tiles));
   c->ratings_set = true;
   return 0;
 }
@@ -651,7 +766,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
   CU(cudaSetDevice(c->cfg.device));
   const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
   Side &s = theta_side ? c->th : c->be;
-  const uint32_t R = s.R, K = c->K, Kp = c->Kp;
+  const uint32_t R = s.R, K = c->K, Kp = c->Kp, ld = c->ld;
   double *d0 = nullptr, *d1 = nullptr, *d2 = nullptr, *d3 = nullptr;
   int rc = 0;
   switch (which) {
@@ -662,11 +777,11 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
     const uint32_t g = s.update_grid;
     if ((rc = stage_in(c, shape, rk, &d0)) || (rc = stage_in(c, rate, c->hier ? rk : K, &d1)) ||
         (rc = stage_in(c, Ev, rk, &d2)) || (rc = stage_in(c, Elogv, rk, &d3))) break;
-    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d0, R, K, Kp, s.shape, 0.f);
-    if (c->hier) import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d1, R, K, Kp, s.rate, 1.f);
-    else import_matrix_kernel<<<1, kUpdateWarps * 32, 0, c->stream>>>(d1, 1, K, Kp, s.rate, 1.f);
-    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d2, R, K, Kp, s.Ev, 0.f);
-    import_elog_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d3, R, K, Kp, s.Elog, s.A, s.shift);
+    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d0, R, K, Kp, ld, s.shape, 0.f);
+    if (c->hier) import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d1, R, K, Kp, ld, s.rate, 1.f);
+    else import_matrix_kernel<<<1, kUpdateWarps * 32, 0, c->stream>>>(d1, 1, K, Kp, ld, s.rate, 1.f);
+    import_matrix_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d2, R, K, Kp, ld, s.Ev, 0.f);
+    import_elog_kernel<<<g, kUpdateWarps * 32, 0, c->stream>>>(d3, R, K, Kp, ld, s.Elog, s.A, s.shift);
     c->launches += 4;
     if ((rc = refresh_colsum(c, s))) break;
     s.have_state = true;
@@ -721,14 +836,14 @@ int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev
   CU(cudaSetDevice(c->cfg.device));
   const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
   Side &s = theta_side ? c->th : c->be;
-  const uint32_t R = s.R, K = c->K, Kp = c->Kp;
+  const uint32_t R = s.R, K = c->K, ld = c->ld;
   double *stage = nullptr;
   const size_t rk = (size_t)R * K;
   CU(cudaMalloc((void **)&stage, std::max<size_t>(rk, 16) * sizeof(double)));
   cudaError_t e = cudaSuccess;
   auto out_matrix = [&](const float *src, double *dst, uint32_t rows) {
     if (!dst || e != cudaSuccess) return;
-    export_matrix_kernel<<<row_grid(c, rows), kUpdateWarps * 32, 0, c->stream>>>(src, rows, K, Kp, stage);
+    export_matrix_kernel<<<row_grid(c, rows), kUpdateWarps * 32, 0, c->stream>>>(src, rows, K, ld, stage);
     c->launches++;
     e = cudaMemcpyAsync(dst, stage, (size_t)rows * K * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -849,7 +964,7 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
     a.u = du; a.i = di; a.y = dy; a.npairs = npairs;
     a.Et = c->th.Ev; a.Eb = c->be.Ev;
     a.Etb = c->bias ? c->th.b_Ev : nullptr; a.Ebb = c->bias ? c->be.b_Ev : nullptr;
-    a.K4 = c->K4; a.binary = c->binary; a.logfact = c->logfact; a.block_sums = c->ll_blocks;
+    a.K4 = c->K4; a.ld4 = c->ld / 4; a.binary = c->binary; a.logfact = c->logfact; a.block_sums = c->ll_blocks;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * 8, (npairs * 8 + kSweepThreads - 1) / kSweepThreads);
     // fixed mapping: 8 lanes per pair, up to 8 float4 per lane covers K <= 256; wider K uses 32 lanes
     if (c->K4 <= 64) heldout_kernel<8, 8><<<grid, kSweepThreads, 0, c->stream>>>(a);

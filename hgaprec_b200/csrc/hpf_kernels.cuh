@@ -73,23 +73,24 @@ struct SweepArgs {
   uint32_t R;              // rows on the row side
   const uint32_t *idx;     // per nonzero: row number on the column side
   const uint8_t *y;        // per nonzero rating, or nullptr (all ones)
-  const float *Arow;       // [R x Kp]  exp(Elog - shift), row side
-  const float *Acol;       // [C x Kp]  same, column side
-  float *T;                // [R x Kp]  out: sum (y/Z) * Acol
-  float *Tpart;            // [P x Kp]  out: partial sums of multi-segment rows
+  const float *Arow;       // [R x ld]  exp(Elog - shift), row side
+  const float *Acol;       // [C x ld]  same, column side
+  float *T;                // [R x ld]  out: sum (y/Z) * Acol
+  float *Tpart;            // [P x ld]  out: partial sums of multi-segment rows
   // -bias (phi has K+2 slots, hgaprec.cc:222-239)
   const float2 *row_aux;   // {exp(Elogbias_r - shift_r), exp(-shift_r)}
   const float2 *col_aux;
   float *Tb;               // [R] out: sum (y/Z) * col_aux.y
   float *Tbpart;           // [P]
   // exact fallback
-  const float *ElogRow, *ElogCol;   // [. x Kp], padding = -inf
+  const float *ElogRow, *ElogCol;   // [. x ld], padding = -inf
   const float *ElogbRow, *ElogbCol; // bias logs (or nullptr)
-  float *Tdirect;          // [R x Kp] += y*phi
+  float *Tdirect;          // [R x ld] += y*phi
   float *Tbdirect;         // [R]
   uint32_t *direct_flag;   // set to 1 when Tdirect was touched
   unsigned long long *slow_count;
-  uint32_t K, Kp, K4;
+  uint32_t K, K4;  // factors; float4 per row that hold data (K rounded up to 4)
+  uint32_t ld, ld4; // row stride of every matrix in floats / float4 (rows are 128-byte aligned)
 };
 
 template <int G>
@@ -107,7 +108,7 @@ struct SlowArgs { // by value: taking the address of kernel parameters would for
   float *Tdirect, *Tbdirect;
   uint32_t *direct_flag;
   unsigned long long *slow_count;
-  uint32_t K, Kp, K4;
+  uint32_t K, K4, ld, ld4;
 };
 
 template <int G, int V, bool BIAS>
@@ -115,8 +116,8 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
 {
   const int gl = lane & (G - 1);
   const uint32_t mask = group_mask<G>(lane);
-  const float4 *er = reinterpret_cast<const float4 *>(a.ElogRow) + (size_t)row * a.K4;
-  const float4 *ec = reinterpret_cast<const float4 *>(a.ElogCol) + (size_t)c * a.K4;
+  const float4 *er = reinterpret_cast<const float4 *>(a.ElogRow) + (size_t)row * a.ld4;
+  const float4 *ec = reinterpret_cast<const float4 *>(a.ElogCol) + (size_t)c * a.ld4;
   float mx = -CUDART_INF_F;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -147,7 +148,7 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
 #pragma unroll
   for (int off = G / 2; off >= 1; off >>= 1) sum += __shfl_xor_sync(mask, sum, off);
   const float sc = yv / sum;
-  float *td = a.Tdirect + (size_t)row * a.Kp;
+  float *td = a.Tdirect + (size_t)row * a.ld;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const uint32_t q = gl + v * G;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 
   float4 ar[V], acc[V];
   {
-    const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.K4;
+    const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.ld4;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const uint32_t q = gl + v * G;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
     const bool active = j < len;
 
     float4 b[V];
-    const float4 *cp = acol + (size_t)c * a.K4;
+    const float4 *cp = acol + (size_t)c * a.ld4;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const uint32_t q = gl + v * G;
@@ -253,15 +254,15 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         SlowArgs sa;
         sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
         sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
-        sa.slow_count = a.slow_count; sa.K = a.K; sa.Kp = a.Kp; sa.K4 = a.K4;
+        sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
         sweep_slow_path<G, V, BIAS>(sa, row, c, (float)yv, lane);
       }
     }
   }
 
   if (have) {
-    float4 *dst = reinterpret_cast<float4 *>(out < a.R ? a.T + (size_t)out * a.Kp
-                                                        : a.Tpart + (size_t)(out - a.R) * a.Kp);
+    float4 *dst = reinterpret_cast<float4 *>(out < a.R ? a.T + (size_t)out * a.ld
+                                                        : a.Tpart + (size_t)(out - a.R) * a.ld);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const uint32_t q = gl + v * G;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 // ---------------------------------------------------------------------------
 struct CombineArgs {
   const uint32_t *multi_row, *multi_first, *multi_cnt;
-  uint32_t nmulti, Kp;
+  uint32_t nmulti, Kp, ld; // Kp: K rounded up to 4 (loop bound); ld: row stride in floats
   const float *Tpart;
   float *T;
   const float *Tbpart; // or nullptr
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const Combin
   float *mine = sm + (size_t)w * a.Kp;
   for (uint32_t k = lane; k < a.Kp; k += 32) {
     float s = 0.f;
-    for (uint32_t p = w; p < cnt; p += kUpdateWarps) s += a.Tpart[(size_t)(first + p) * a.Kp + k];
+    for (uint32_t p = w; p < cnt; p += kUpdateWarps) s += a.Tpart[(size_t)(first + p) * a.ld + k];
     mine[k] = s;
   }
   float *smb = sm + (size_t)kUpdateWarps * a.Kp;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const Combin
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < kUpdateWarps; ++q) s += sm[(size_t)q * a.Kp + k];
-    a.T[(size_t)row * a.Kp + k] = s;
+    a.T[(size_t)row * a.ld + k] = s;
   }
   if (a.Tbpart != nullptr && threadIdx.x == 0) {
     float s = 0.f;
@@ -330,11 +331,11 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const Combin
 // (hgaprec.cc:1388-1396) and the next iteration's shifted exponentials.
 // ---------------------------------------------------------------------------
 struct UpdateArgs {
-  uint32_t R, K, Kp;
+  uint32_t R, K, Kp, ld; // Kp: K rounded up to 4; ld: row stride in floats
   const float *T;
   float *Tdirect;
   const uint32_t *direct_flag;
-  float *A, *Elog, *Ev, *shape, *rate; // rate: [R x Kp] (hier) or [Kp] (global rate)
+  float *A, *Elog, *Ev, *shape, *rate; // rate: [R x ld] (hier) or [Kp] (global rate)
   float *shift;                        // [R]
   int hier;
   const float *colsum_other; // [Kp]  sum over the OTHER side's rows of Ev
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
       a.rate[k] = k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f;
 
   for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < a.R; r += warps_total) {
-    const size_t base = (size_t)r * a.Kp;
+    const size_t base = (size_t)r * a.ld;
     const float rprior = a.hier ? a.pr_Ev[r] : a.prior_rate;
     float mx = -CUDART_INF_F, rowsum = 0.f;
     for (uint32_t k = lane; k < a.Kp; k += 32) {
@@ -465,7 +466,7 @@ __global__ void colsum_finalize_kernel(const float *partial, uint32_t nblocks, u
 
 // column sums of an existing Ev matrix (after hpf_set_state)
 __global__ void __launch_bounds__(kUpdateWarps * 32) colsum_partial_kernel(const float *Ev, uint32_t R, uint32_t Kp,
-                                                                          float *partial)
+                                                                          uint32_t ld, float *partial)
 {
   extern __shared__ float cs[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) colsum_partial_kernel(const
   for (uint32_t k = lane; k < Kp; k += 32) mycs[k] = 0.f;
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
   for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
-    for (uint32_t k = lane; k < Kp; k += 32) mycs[k] += Ev[(size_t)r * Kp + k];
+    for (uint32_t k = lane; k < Kp; k += 32) mycs[k] += Ev[(size_t)r * ld + k];
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < Kp; k += blockDim.x) {
     float s = 0.f;
@@ -484,21 +485,21 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) colsum_partial_kernel(const
 }
 
 // ---------------------------------------------------------------------------
-// state import / export (host fp64 row-major, stride K  <->  device fp32, stride Kp)
+// state import / export (host fp64 row-major, stride K  <->  device fp32, stride ld)
 // ---------------------------------------------------------------------------
 // matrix import; when Elog != nullptr also derives shift and A in double.
 __global__ void __launch_bounds__(kUpdateWarps * 32) import_matrix_kernel(const double *src, uint32_t R, uint32_t K, uint32_t Kp,
-                                                                         float *dst, float pad)
+                                                                         uint32_t ld, float *dst, float pad)
 {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
   for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
     for (uint32_t k = lane; k < Kp; k += 32)
-      dst[(size_t)r * Kp + k] = k < K ? (float)src[(size_t)r * K + k] : pad;
+      dst[(size_t)r * ld + k] = k < K ? (float)src[(size_t)r * K + k] : pad;
 }
 
 __global__ void __launch_bounds__(kUpdateWarps * 32) import_elog_kernel(const double *src, uint32_t R, uint32_t K, uint32_t Kp,
-                                                                       float *Elog, float *A, float *shift)
+                                                                       uint32_t ld, float *Elog, float *A, float *shift)
 {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
@@ -512,11 +513,11 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) import_elog_kernel(const do
     for (uint32_t k = lane; k < Kp; k += 32) {
       if (k < K) {
         const double e = src[(size_t)r * K + k];
-        Elog[(size_t)r * Kp + k] = (float)e;
-        A[(size_t)r * Kp + k] = (float)exp(e - (double)mxf);
+        Elog[(size_t)r * ld + k] = (float)e;
+        A[(size_t)r * ld + k] = (float)exp(e - (double)mxf);
       } else {
-        Elog[(size_t)r * Kp + k] = -CUDART_INF_F;
-        A[(size_t)r * Kp + k] = 0.f;
+        Elog[(size_t)r * ld + k] = -CUDART_INF_F;
+        A[(size_t)r * ld + k] = 0.f;
       }
     }
     if (lane == 0) shift[r] = mxf;
@@ -536,13 +537,13 @@ __global__ void build_aux_kernel(const float *b_Elog, const float *shift, uint32
   if (r < R) aux[r] = make_float2(expf(b_Elog[r] - shift[r]), expf(-shift[r]));
 }
 
-__global__ void __launch_bounds__(kUpdateWarps * 32) export_matrix_kernel(const float *src, uint32_t R, uint32_t K, uint32_t Kp,
+__global__ void __launch_bounds__(kUpdateWarps * 32) export_matrix_kernel(const float *src, uint32_t R, uint32_t K, uint32_t ld,
                                                                          double *dst)
 {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
   for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < R; r += warps_total)
-    for (uint32_t k = lane; k < K; k += 32) dst[(size_t)r * K + k] = (double)src[(size_t)r * Kp + k];
+    for (uint32_t k = lane; k < K; k += 32) dst[(size_t)r * K + k] = (double)src[(size_t)r * ld + k];
 }
 
 __global__ void export_vector_kernel(const float *src, uint32_t n, double *dst)
@@ -566,9 +567,9 @@ struct HeldoutArgs {
   const uint32_t *u, *i;
   const uint8_t *y;
   uint64_t npairs;
-  const float *Et, *Eb;   // Ev matrices [. x Kp]
+  const float *Et, *Eb;   // Ev matrices [. x ld]
   const float *Etb, *Ebb; // bias Ev (or nullptr)
-  uint32_t K4;
+  uint32_t K4, ld4;
   int binary;
   const double *logfact;  // [256]  log(y!) as the reference sums it (hgaprec.cc:1563-1570)
   double *block_sums;     // [gridDim.x]
@@ -587,8 +588,8 @@ __global__ void __launch_bounds__(kSweepThreads) heldout_kernel(const HeldoutArg
     const uint64_t p = g0 + rd * groups_total;
     const bool active = p < a.npairs;
     const uint32_t uu = active ? a.u[p] : 0u, ii = active ? a.i[p] : 0u;
-    const float4 *tp = reinterpret_cast<const float4 *>(a.Et) + (size_t)uu * a.K4;
-    const float4 *bp = reinterpret_cast<const float4 *>(a.Eb) + (size_t)ii * a.K4;
+    const float4 *tp = reinterpret_cast<const float4 *>(a.Et) + (size_t)uu * a.ld4;
+    const float4 *bp = reinterpret_cast<const float4 *>(a.Eb) + (size_t)ii * a.ld4;
     float dot = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -635,7 +636,11 @@ __global__ void sum_blocks_kernel(const double *block_sums, uint32_t nblocks, do
 }
 
 // ---------------------------------------------------------------------------
-// ratings set-up: CSR -> CSC helpers (the sort itself is cub::DeviceRadixSort)
+// ratings set-up.  Both sweeps walk the nonzeros grouped by (tile of the
+// GATHERED side, row): a tile is a contiguous range of gathered rows whose
+// factor rows fit the L2 budget, so every gather of a tile's pass is an L2 hit.
+// The orderings are built with cub stable radix sorts of a permutation; these
+// kernels produce the keys and apply the permutation.
 // ---------------------------------------------------------------------------
 __global__ void expand_rows_kernel(const uint64_t *row_ptr, uint32_t nrows, uint64_t nnz, uint32_t *row_of)
 {
@@ -655,25 +660,43 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n)
   if (j < n) p[j] = (uint32_t)j;
 }
 
-__global__ void gather_csc_kernel(const uint32_t *perm, const uint32_t *row_of, const uint8_t *y, uint64_t nnz,
-                                  uint32_t *csc_row, uint8_t *csc_y)
+// key[j] = src[perm[j]] / div   (div == 1: plain gather)
+__global__ void gather_key_kernel(const uint32_t *perm, const uint32_t *src, uint32_t div, uint64_t nnz, uint32_t *key)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) key[j] = src[perm[j]] / div;
+}
+
+// apply the final permutation: gathered-side index, rating, and the composite
+// key tile * R + row that the run pointers are derived from
+__global__ void apply_perm_kernel(const uint32_t *perm, const uint32_t *row, const uint32_t *col, const uint8_t *y,
+                                  uint32_t tile_cols, uint32_t R, uint64_t nnz, uint32_t *out_idx, uint8_t *out_y,
+                                  uint32_t *out_key)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
   const uint32_t p = perm[j];
-  csc_row[j] = row_of[p];
-  if (y != nullptr) csc_y[j] = y[p];
+  const uint32_t cc = col[p];
+  out_idx[j] = cc;
+  if (y != nullptr) out_y[j] = y[p];
+  out_key[j] = (cc / tile_cols) * R + row[p];
 }
 
-// col_ptr[c] = first position whose sorted key is >= c
-__global__ void col_ptr_kernel(const uint32_t *sorted_col, uint64_t nnz, uint32_t ncols, uint64_t *col_ptr)
+// run_ptr[c] = first position whose sorted key is >= c, for c in [0, nkeys]
+__global__ void run_ptr_kernel(const uint32_t *sorted_key, uint64_t nnz, uint32_t nkeys, uint64_t *run_ptr)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > nnz) return;
-  const uint32_t prev = j == 0 ? 0u : sorted_col[j - 1] + 1u;
-  const uint32_t cur = j == nnz ? ncols + 1u : sorted_col[j] + 1u;
-  // keys in (prev-1, cur-1] start at j
-  for (uint32_t c = (j == 0 ? 0u : prev); c < cur && c <= ncols; ++c) col_ptr[c] = j;
+  const uint32_t prev = j == 0 ? 0u : sorted_key[j - 1] + 1u;
+  const uint32_t cur = j == nnz ? nkeys + 1u : sorted_key[j] + 1u;
+  for (uint32_t c = prev; c < cur && c <= nkeys; ++c) run_ptr[c] = j;
+}
+
+// any index >= limit?  (argument check of hpf_set_ratings_csr, done on the device)
+__global__ void check_range_kernel(const uint32_t *idx, uint64_t nnz, uint32_t limit, uint32_t *bad)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz && idx[j] >= limit) atomicMax(bad, idx[j]);
 }
 
 } // namespace hpf

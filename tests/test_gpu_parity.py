@@ -136,6 +136,21 @@ def test_empty_rows_long_rows_duplicates_and_big_ratings():
     assert not bad, bad
 
 
+@pytest.mark.parametrize("flags,tile_kb", [(H.HIER, 64), (H.HIER | H.BIAS, 200), (H.BIAS, 37)])
+def test_l2_tiled_orderings_match_oracle(monkeypatch, flags, tile_kb):
+    """Both sweeps regroup the nonzeros by (tile of the gathered side, row) once
+    the gathered factor rows exceed the L2 budget; force many tiles on a small
+    problem (also: split rows inside tiles) and compare with the oracle."""
+    monkeypatch.setenv("HPF_L2_TILE_KB", str(tile_kb))
+    monkeypatch.setenv("HPF_SEG_LEN", "32")
+    d, s = _oracle_case(3000, 1500, 200000, 100, flags, seed=31)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 2, nthreads=8)
+    got, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 2)
+    bad = util.compare_states(got, want, rel=4e-5, elog_abs=4e-5)
+    assert not bad, bad
+    assert st["slow_path_nnz"] == 0
+
+
 def test_no_ratings_at_all_and_y_null():
     n, m, k = 10, 12, 4
     s = O.OracleState(n, m, k, 0).init(2)
