@@ -13,13 +13,13 @@ fi
 timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-  KREGEX='regex:sweep|update_kernel|combine|colsum|beta|theta|hpf'
+  KREGEX='regex:hpf::'
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 400 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 \
       > gpurun_out/bench_under_ncu.log 2>&1
   echo "ncu list exit $?"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k "${NCU_FULL_K:-regex:sweep}" \
-      --launch-skip ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -o gpurun_out/sweep_full -f \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k "${NCU_FULL_K:-regex:sweep_kernel|update_kernel}" \
+      --launch-skip ${NCU_SKIP:-8} -c ${NCU_COUNT:-4} -o gpurun_out/sweep_full -f \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
