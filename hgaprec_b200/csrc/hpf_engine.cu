@@ -19,8 +19,10 @@
 // ratings in both orientations (CSR for the user pass, CSC for the item pass).
 #include "../../include/hpf_cuda.h"
 #include "hpf_kernels.cuh"
+#include "hpf_topn.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cudaTypedefs.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -979,9 +981,111 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
   return 0;
 }
 
-int hpf_topn(hpf_ctx *c, const uint32_t *, uint32_t, const uint64_t *, const uint32_t *, uint32_t, uint32_t *, float *)
+int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx,
+             uint32_t topn, uint32_t *items_out, float *scores_out)
 {
-  return fail(c, HPF_EINVAL, "hpf_topn: not implemented in this build");
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  if (nu == 0) return 0;
+  if (!users || !items_out || !scores_out) return fail(c, HPF_EINVAL, "null argument");
+  if (topn == 0 || topn > (uint32_t)topk::kMaxTopN) return fail(c, HPF_EINVAL, "topn=%u out of range [1,%d]", topn, topk::kMaxTopN);
+  if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
+  if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
+  CU(cudaSetDevice(c->cfg.device));
+  const uint32_t n = c->th.R, m = c->be.R;
+  for (uint32_t a = 0; a < nu; ++a)
+    if (users[a] >= n) return fail(c, HPF_EINVAL, "users[%u]=%u >= n_users=%u", a, users[a], n);
+  const uint64_t nex = excl_ptr ? excl_ptr[nu] : 0;
+  if (excl_ptr) {
+    if (excl_ptr[0] != 0) return fail(c, HPF_EINVAL, "excl_ptr[0] must be 0");
+    for (uint32_t a = 0; a < nu; ++a)
+      if (excl_ptr[a + 1] < excl_ptr[a]) return fail(c, HPF_EINVAL, "excl_ptr not monotone at %u", a);
+    if (nex > 0 && !excl_idx) return fail(c, HPF_EINVAL, "excl_idx is null");
+  }
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void *fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const uint32_t Kext = c->K + (c->bias ? 2u : 0u);
+  const uint32_t Kpad = (Kext + topk::kBlockK - 1) / topk::kBlockK * topk::kBlockK;
+  const uint32_t m_pad = (m + topk::kTileN - 1) / topk::kTileN * topk::kTileN;
+  const uint32_t chunk_users = 2048u * topk::kTileM; // bounds the candidate scratch to 1 GiB per launch
+  const uint32_t nu_cap = std::min<uint64_t>(((uint64_t)nu + topk::kTileM - 1) / topk::kTileM * topk::kTileM, chunk_users);
+
+  Scratch tmp;
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  uint32_t *d_users = nullptr, *d_exidx = nullptr, *d_rowof = nullptr, *d_items = nullptr;
+  uint64_t *d_exptr = nullptr, *d_key = nullptr, *d_key2 = nullptr;
+  unsigned long long *d_cand = nullptr;
+  float *d_scores = nullptr;
+  CU(tmp.get(&a_hi, (size_t)nu_cap * Kpad)); CU(tmp.get(&a_lo, (size_t)nu_cap * Kpad));
+  CU(tmp.get(&b_hi, (size_t)m_pad * Kpad)); CU(tmp.get(&b_lo, (size_t)m_pad * Kpad));
+  CU(tmp.get(&d_users, nu)); CU(tmp.get(&d_exptr, (size_t)nu + 1));
+  CU(tmp.get(&d_cand, (size_t)nu_cap * topk::kCap));
+  CU(tmp.get(&d_items, (size_t)nu_cap * topn)); CU(tmp.get(&d_scores, (size_t)nu_cap * topn));
+  CU(cudaMemcpyAsync(d_users, users, (size_t)nu * 4, cudaMemcpyHostToDevice, c->stream));
+  if (excl_ptr) CU(cudaMemcpyAsync(d_exptr, excl_ptr, ((size_t)nu + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  else CU(cudaMemsetAsync(d_exptr, 0, ((size_t)nu + 1) * 8, c->stream));
+  if (nex > 0) {
+    // exclusion lists sorted by (user position, item) so the epilogue can binary-search them
+    CU(tmp.get(&d_exidx, nex)); CU(tmp.get(&d_rowof, nex)); CU(tmp.get(&d_key, nex)); CU(tmp.get(&d_key2, nex));
+    CU(cudaMemcpyAsync(d_exidx, excl_idx, nex * 4, cudaMemcpyHostToDevice, c->stream));
+    const unsigned nb = (unsigned)((nex + 255) / 256);
+    CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
+    check_range_kernel<<<nb, 256, 0, c->stream>>>(d_exidx, nex, m, c->scratch_u32);
+    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
+    topk::excl_key_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, d_exidx, nex, d_key);
+    c->launches += 3;
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
+    size_t tmp_bytes = 0;
+    void *d_tmp = nullptr;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)nex, 0, 64, c->stream);
+    CU(tmp.get((char **)&d_tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, (const uint64_t *)d_key, d_key2, (int64_t)nex, 0, 32 + bits_for(nu), c->stream));
+    topk::excl_unkey_kernel<<<nb, 256, 0, c->stream>>>(d_key2, nex, d_exidx);
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad != 0) return fail(c, HPF_EINVAL, "excl_idx holds item %u >= n_items=%u", bad, m);
+  }
+  // item-side operands: hi / lo split of E[beta] (+ {1, E[betabias]})
+  topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->be.Ev, c->ld, c->K, c->bias ? c->be.b_Ev : nullptr, 0, nullptr, m,
+                                                         m_pad, Kpad, b_hi, b_lo);
+  c->launches++;
+  CU(cudaGetLastError());
+  auto make_map = [&](CUtensorMap *map, void *ptr, uint64_t rows, uint32_t box_rows) -> bool {
+    cuuint64_t dims[2] = { Kpad, rows };
+    cuuint64_t strides[1] = { (cuuint64_t)Kpad * 2 };
+    cuuint32_t box[2] = { (cuuint32_t)topk::kBlockK, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  if (!make_map(&map_b_hi, b_hi, m_pad, topk::kTileN) || !make_map(&map_b_lo, b_lo, m_pad, topk::kTileN))
+    return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the item operand");
+  CU(cudaFuncSetAttribute(topk::topn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk::kSmemBytes));
+  for (uint32_t u0 = 0; u0 < nu; u0 += chunk_users) {
+    const uint32_t cu = std::min(chunk_users, nu - u0);
+    const uint32_t cu_pad = (cu + topk::kTileM - 1) / topk::kTileM * topk::kTileM;
+    topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.Ev, c->ld, c->K, c->bias ? c->th.b_Ev : nullptr, 1, d_users + u0,
+                                                           cu, cu_pad, Kpad, a_hi, a_lo);
+    if (!make_map(&map_a_hi, a_hi, cu_pad, topk::kTileM) || !make_map(&map_a_lo, a_lo, cu_pad, topk::kTileM))
+      return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the user operand");
+    topk::TopnArgs a;
+    a.nu = cu; a.m = m; a.nkb = Kpad / topk::kBlockK; a.ntiles_n = m_pad / topk::kTileN; a.topn = topn;
+    a.excl_ptr = d_exptr + u0; a.excl_sorted = d_exidx; a.cand = d_cand; a.items_out = d_items; a.scores_out = d_scores;
+    topk::topn_kernel<<<cu_pad / topk::kTileM, topk::kThreads, topk::kSmemBytes, c->stream>>>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, a);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(items_out + (size_t)u0 * topn, d_items, (size_t)cu * topn * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(scores_out + (size_t)u0 * topn, d_scores, (size_t)cu * topn * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
 }
 
 int hpf_comm_unique_id(void *id_out, size_t id_bytes)

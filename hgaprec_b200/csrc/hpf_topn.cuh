@@ -1,0 +1,444 @@
+// hpf_topn.cuh -- K7: -gen-ranking scoring + mask + per-user top-N on sm_100a.
+//
+// Replaces the scoring loop of HGAPRec::compute_precision (hgaprec.cc:1725-1763)
+// and prediction_score[_hier] (1850-1880, 1969-1991): for every listed user the
+// score of EVERY item, E[theta_u] . E[beta_i] (+ E[thetabias_u] + E[betabias_i]),
+// items of the user's exclusion list (training U validation) forced to 0.0, then
+// the first topn of the descending sort (sort_by_value, matrix.hh:253-257).
+//
+// This is the one dense contraction of the path, so it runs on the 5th-gen
+// tensor cores.  fp32 fidelity of the ranking is kept with a split-bf16 product:
+//   x = hi + lo (two bf16),  a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
+// (three tcgen05.mma kind::f16 passes into the same fp32 TMEM accumulator; the
+// dropped a_lo.b_lo term is ~2^-16 relative).  The bias terms ride in two extra
+// K columns ([.., bias_u, 1] . [.., 1, bias_i]).
+//
+// One CTA owns 128 users (the UMMA M) and streams all items in tiles of 256 (the
+// UMMA N), double-buffered in TMEM (2 x 256 columns):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D, 128B-swizzled K-major
+//               boxes of the hi / lo operand matrices into a 2-stage smem ring
+//   warp 1      TMEM allocator + the single thread that issues tcgen05.mma
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, one THREAD per user
+//               row; a score is kept only if it beats the row's running
+//               threshold (the topn-th best so far), so the 8.5e9 scores of the
+//               Netflix-scale problem are never materialised.  Survivors go to
+//               a per-row candidate buffer in global memory (L2 resident); when
+//               a buffer runs full the warp selects the topn-th largest key with
+//               a bitwise count-select in registers and compacts.
+// Keys are 64 bit, (score bits << 32) | ~item: scores are >= 0 so the float bits
+// order like the values, all keys are distinct, and "larger key" is exactly
+// "higher score, ties by lower item" -- the order of oracle/hpf_oracle.c.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hpf {
+namespace topk {
+
+constexpr int kTileM = 128;        // users per CTA == UMMA M
+constexpr int kTileN = 256;        // items per accumulator buffer == UMMA N
+constexpr int kBlockK = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kCap = 512;          // candidate slots per user row
+constexpr int kMaxTopN = 256;      // kCap - kTileN
+constexpr int kThreads = 192;      // 6 warps
+constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KB per (hi | lo) box
+constexpr uint32_t kBBytes = kTileN * kBlockK * 2;  // 32 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes; // 96 KB
+constexpr uint32_t kSortBytes = 4 * kMaxTopN * 8;   // final sort buffers, one per epilogue warp
+constexpr uint32_t kSmemBytes = 1024 + kStages * kStageBytes + kSortBytes + 256;
+constexpr unsigned long long kSpinLimit = 1ull << 28;
+
+// ---- PTX wrappers -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug traps (launch failure reported through the ABI) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t done = 0;
+  for (unsigned long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor, K-major operand tile with 128-byte swizzle (what the TMA
+// box writes): rows are 128 B apart, 8-row groups 1024 B apart (SBO), version 1
+// (Blackwell), layout type 2 (SWIZZLE_128B).  The tile base must be 1024-aligned;
+// a K step of 16 bf16 (32 B) inside the swizzle row advances the start address.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr)
+{
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)1u << 16;                 // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)1u << 46;                 // descriptor version
+  d |= (uint64_t)2u << 61;                 // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+// ---- operand preparation ------------------------------------------------------
+// rows [0, rows_pad) x cols [0, Kpad) of hi / lo (bf16, row stride Kpad) from the
+// fp32 expectation matrix Ev (row stride ld).  gather != nullptr picks source rows
+// (the listed users).  With bias two extra columns carry {bias, 1} (users) or
+// {1, bias} (items).  Rows >= rows and the K padding are zero.
+__global__ void __launch_bounds__(256) split_kernel(const float *Ev, uint32_t ld, uint32_t K, const float *bias_ev,
+                                                    int bias_first, const uint32_t *gather, uint32_t rows,
+                                                    uint32_t rows_pad, uint32_t Kpad, __nv_bfloat16 *hi,
+                                                    __nv_bfloat16 *lo)
+{
+  const uint64_t total = (uint64_t)rows_pad * Kpad;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(e / Kpad), k = (uint32_t)(e % Kpad);
+    float v = 0.f;
+    if (r < rows) {
+      const uint32_t src = gather ? gather[r] : r;
+      if (k < K) v = Ev[(size_t)src * ld + k];
+      else if (bias_ev != nullptr && k == K) v = bias_first ? bias_ev[src] : 1.f;
+      else if (bias_ev != nullptr && k == K + 1) v = bias_first ? 1.f : bias_ev[src];
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// key[j] = (row_of[j] << 32) | idx[j]   (exclusion entries, sorted by cub afterwards)
+__global__ void excl_key_kernel(const uint32_t *row_of, const uint32_t *idx, uint64_t cnt, uint64_t *key)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cnt) key[j] = ((uint64_t)row_of[j] << 32) | idx[j];
+}
+__global__ void excl_unkey_kernel(const uint64_t *key, uint64_t cnt, uint32_t *idx)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cnt) idx[j] = (uint32_t)key[j];
+}
+
+// ---- the scoring + selection kernel -------------------------------------------
+struct TopnArgs {
+  uint32_t nu;          // users of this launch (rows >= nu are padding)
+  uint32_t m;           // items
+  uint32_t nkb;         // K blocks of 64
+  uint32_t ntiles_n;    // item tiles of 256
+  uint32_t topn;
+  const uint64_t *excl_ptr; // [nu + 1] into excl_sorted (already offset to this launch's first user)
+  const uint32_t *excl_sorted; // per user ascending item ids
+  unsigned long long *cand;    // [gridDim.x * 128 * kCap]
+  uint32_t *items_out;  // [nu x topn]
+  float *scores_out;    // [nu x topn]
+};
+
+__device__ __forceinline__ bool is_excluded(const uint32_t *lst, uint32_t len, uint32_t item)
+{
+  uint32_t lo = 0, hi = len;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t v = __ldg(lst + mid);
+    if (v == item) return true;
+    if (v < item) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// Warp-cooperative: among the cnt (<= kCap) keys of one row keep the `keep`
+// largest (keep <= cnt), compacted to the front of buf in arbitrary order;
+// returns the smallest kept key (the row's new threshold).  Keys are distinct.
+__device__ __forceinline__ unsigned long long warp_select(unsigned long long *buf, uint32_t cnt, uint32_t keep, int lane)
+{
+  constexpr int PER = kCap / 32;
+  unsigned long long k[PER];
+  unsigned long long all_or = 0ull, all_and = ~0ull;
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const uint32_t j = lane + 32 * t;
+    k[t] = j < cnt ? buf[j] : 0ull; // 0 never beats a real key: real keys have ~item != 0 unless item == 2^32-1
+    if (j < cnt) { all_or |= k[t]; all_and &= k[t]; }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    all_or |= __shfl_xor_sync(0xffffffffu, all_or, off);
+    all_and &= __shfl_xor_sync(0xffffffffu, all_and, off);
+  }
+  // bits on which the keys differ; the others are fixed in the answer
+  const unsigned long long vary = all_or & ~all_and;
+  unsigned long long thr = all_and; // greedy: largest T with count(key >= T) >= keep
+  for (int b = 63; b >= 0; --b) {
+    if (!((vary >> b) & 1ull)) continue;
+    const unsigned long long trial = thr | (1ull << b);
+    uint32_t c = 0;
+#pragma unroll
+    for (int t = 0; t < PER; ++t) c += (k[t] >= trial) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= keep) thr = trial;
+  }
+  // compact: kept keys to the front (each lane writes its own, offsets by warp scan)
+  uint32_t mine = 0;
+#pragma unroll
+  for (int t = 0; t < PER; ++t) mine += (k[t] >= thr && k[t] != 0ull) ? 1u : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  uint32_t pos = incl - mine;
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < PER; ++t)
+    if (k[t] >= thr && k[t] != 0ull) buf[pos++] = k[t];
+  __syncwarp();
+  return thr;
+}
+
+// bitonic sort (descending) of P = 2^p <= kMaxTopN keys in shared memory by one warp
+__device__ __forceinline__ void warp_sort_desc(unsigned long long *s, uint32_t P, int lane)
+{
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = lane; i < P; i += 32) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = s[i], b = s[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { s[i] = b; s[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+            const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TopnArgs a)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sort_off = kStages * kStageBytes;
+  const uint32_t bar_off = sort_off + kSortBytes;
+  const uint32_t bar_full = base + bar_off;            // [kStages]
+  const uint32_t bar_empty = bar_full + 8 * kStages;   // [kStages]
+  const uint32_t bar_tfull = bar_empty + 8 * kStages;  // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;          // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + bar_off + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_m = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) { // TMEM: all 512 columns (two 256-column accumulators); this warp also frees them
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t j = 0; j < a.ntiles_n; ++j)
+        for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          const uint32_t st = base + s * kStageBytes;
+          mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+          tma_load_2d(st, &map_a_hi, bar_full + 8 * s, (int)(kb * kBlockK), (int)(tile_m * kTileM));
+          tma_load_2d(st + kABytes, &map_a_lo, bar_full + 8 * s, (int)(kb * kBlockK), (int)(tile_m * kTileM));
+          tma_load_2d(st + 2 * kABytes, &map_b_hi, bar_full + 8 * s, (int)(kb * kBlockK), (int)(j * kTileN));
+          tma_load_2d(st + 2 * kABytes + kBBytes, &map_b_lo, bar_full + 8 * s, (int)(kb * kBlockK), (int)(j * kTileN));
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t j = 0; j < a.ntiles_n; ++j) {
+        const uint32_t buf = j & 1u, tph = (j >> 1) & 1u;
+        mbar_wait(bar_tempty + 8 * buf, tph ^ 1u); // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)kTileN;
+        for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st = base + s * kStageBytes;
+          const uint64_t da_hi = make_desc_sw128(st), da_lo = make_desc_sw128(st + kABytes);
+          const uint64_t db_hi = make_desc_sw128(st + 2 * kABytes), db_lo = make_desc_sw128(st + 2 * kABytes + kBBytes);
+#pragma unroll
+          for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 16 * 2) >> 4); // 32 bytes per K step of 16 bf16
+            tc_mma_bf16(d_tmem, da_hi + adv, db_hi + adv, kIdesc, (kb | kk) != 0u);
+            tc_mma_bf16(d_tmem, da_hi + adv, db_lo + adv, kIdesc, 1u);
+            tc_mma_bf16(d_tmem, da_lo + adv, db_hi + adv, kIdesc, 1u);
+          }
+          tc_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs have read it
+        }
+        tc_commit(bar_tfull + 8 * buf);  // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: one thread per user row =====
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const uint32_t row_in_tile = (uint32_t)(q * 32 + lane);
+    const uint32_t row = tile_m * kTileM + row_in_tile;
+    const bool live = row < a.nu;
+    unsigned long long *my = a.cand + (size_t)row * kCap;
+    const uint32_t *ex = nullptr;
+    uint32_t exlen = 0;
+    if (live) {
+      const uint64_t e0 = a.excl_ptr[row], e1 = a.excl_ptr[row + 1];
+      ex = a.excl_sorted + e0;
+      exlen = (uint32_t)(e1 - e0);
+    }
+    unsigned long long tau = 0ull;                 // keys <= tau can no longer make the top-n
+    uint32_t tau_hi = live ? 0u : 0xffffffffu;
+    uint32_t cnt = 0;
+    for (uint32_t j = 0; j < a.ntiles_n; ++j) {
+      const uint32_t buf = j & 1u, tph = (j >> 1) & 1u;
+      mbar_wait(bar_tfull + 8 * buf, tph);
+      tc_fence_after();
+      const uint32_t col0 = j * kTileN;
+      const uint32_t ncols = a.m - col0 < (uint32_t)kTileN ? a.m - col0 : (uint32_t)kTileN;
+      for (uint32_t c = 0; c < kTileN / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + c * 32, r);
+        tc_wait_ld();
+        const uint32_t valid = ncols > c * 32 ? ncols - c * 32 : 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if ((uint32_t)i < valid && r[i] >= tau_hi) { // scores are >= 0: float bits order like the values
+            const uint32_t item = col0 + c * 32 + i;
+            uint32_t bits = r[i];
+            if ((int)bits < 0) bits = 0u;              // -0.0 / rounding noise below zero cannot occur; be safe
+            if (is_excluded(ex, exlen, item)) bits = 0u; // hgaprec.cc:1729-1735: keeps its slot with score 0
+            const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned long long)(~item);
+            if (key > tau) my[cnt++] = key;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * buf);
+      // rows that could overflow during the next tile are pruned now, warp-cooperatively
+      __syncwarp();
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(kCap - kTileN));
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const uint32_t rcnt = __shfl_sync(0xffffffffu, cnt, src);
+        unsigned long long *rb = a.cand + (size_t)(tile_m * kTileM + q * 32 + src) * kCap;
+        const uint32_t keep = rcnt < a.topn ? rcnt : a.topn;
+        const unsigned long long thr = warp_select(rb, rcnt, keep, lane);
+        if (lane == src) {
+          cnt = keep;
+          if (rcnt >= a.topn) { tau = thr; tau_hi = (uint32_t)(thr >> 32); }
+        }
+      }
+    }
+    // final: per row select the topn, sort them, emit
+    __syncwarp();
+    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(gen_base + sort_off) + (size_t)q * kMaxTopN;
+    uint32_t P = 1;
+    while (P < a.topn) P <<= 1;
+    for (int src = 0; src < 32; ++src) {
+      const uint32_t r_row = tile_m * kTileM + q * 32 + src;
+      if (r_row >= a.nu) break;
+      const uint32_t rcnt = __shfl_sync(0xffffffffu, cnt, src);
+      unsigned long long *rb = a.cand + (size_t)r_row * kCap;
+      const uint32_t keep = rcnt < a.topn ? rcnt : a.topn;
+      if (rcnt > keep) warp_select(rb, rcnt, keep, lane);
+      for (uint32_t i = lane; i < P; i += 32) sbuf[i] = i < keep ? rb[i] : 0ull;
+      __syncwarp();
+      warp_sort_desc(sbuf, P, lane);
+      for (uint32_t i = lane; i < a.topn; i += 32) {
+        const unsigned long long key = sbuf[i];
+        const bool have = i < keep;
+        a.items_out[(size_t)r_row * a.topn + i] = have ? ~(uint32_t)key : 0xffffffffu;
+        a.scores_out[(size_t)r_row * a.topn + i] = have ? __uint_as_float((uint32_t)(key >> 32)) : 0.f;
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+} // namespace topk
+} // namespace hpf

@@ -239,3 +239,70 @@ def test_full_size_netflix_shape_mass_conservation():
     np.testing.assert_allclose((th - 0.3).sum(1), ysum_u, rtol=2e-5, atol=1e-3)
     np.testing.assert_allclose((be - 0.3).sum(1), ysum_i, rtol=2e-5, atol=1e-3)
     assert np.isfinite(th).all() and np.isfinite(be).all()
+
+
+# ------------------------------------------------ -gen-ranking: scoring + top-N
+def _check_topn(items, scores, o_items, o_scores, m, topn, rel=1e-4):
+    """Engine (split-bf16 tensor-core scores, fp32) against the fp64 oracle:
+    the sorted score lists agree to `rel`, and the item at a position agrees
+    wherever the oracle's score there is separated from its neighbours by more
+    than the tolerance (near-ties may legitimately swap)."""
+    kk = min(topn, m)
+    np.testing.assert_allclose(scores[:, :kk], o_scores[:, :kk], rtol=rel, atol=1e-12)
+    if topn > m:
+        assert (items[:, m:] == 0xFFFFFFFF).all() and (scores[:, m:] == 0).all()
+    gap_hi = np.abs(np.diff(o_scores[:, :kk], axis=1, prepend=np.inf))
+    # the list's last entry competes with an item we do not see: never "clear"
+    gap_lo = np.abs(np.diff(o_scores[:, :kk], axis=1, append=o_scores[:, kk - 1:kk]))
+    clear = (np.minimum(gap_hi, gap_lo) > 4 * rel * np.abs(o_scores[:, :kk])) & (o_scores[:, :kk] > 0)
+    assert clear.mean() > 0.2
+    assert (items[:, :kk][clear] == o_items[:, :kk][clear]).all()
+    zero = o_scores[:, :kk] == 0  # excluded items: exact zeros, ties broken by ascending item
+    if kk == m:
+        assert (items[:, :kk][zero] == o_items[:, :kk][zero]).all() and (scores[:, :kk][zero] == 0).all()
+    overlap = np.mean([len(set(a[:kk]) & set(b[:kk])) / kk for a, b in zip(items, o_items)])
+    assert overlap >= 0.99, overlap
+
+
+@pytest.mark.parametrize("name,n,m,nnz,k,flags,topn,iters", [
+    ("hier K=100 top-100", 700, 1000, 40000, 100, H.HIER, 100, 2),
+    ("bpf bias K=20 top-10", 300, 530, 9000, 20, H.BIAS, 10, 2),
+    ("hier bias K=64 top-256, m < topn", 150, 200, 3000, 64, H.HIER | H.BIAS, 256, 1),
+    ("hier K=130 (3 K-blocks) top-50", 260, 777, 12000, 130, H.HIER, 50, 1),
+])
+def test_topn_matches_oracle(name, n, m, nnz, k, flags, topn, iters):
+    d, s = _oracle_case(n, m, nnz, k, flags, seed=17)
+    s.iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8)  # a fitted-looking state
+    rng = np.random.default_rng(5)
+    users = rng.permutation(n)[: max(1, (2 * n) // 3)].astype(np.uint32)
+    users[3] = users[0]  # a user may be listed twice
+    rp = d["row_ptr"].astype(np.int64)
+    excl = [d["col_idx"][rp[u]:rp[u + 1]] for u in users]  # training items, file order (unsorted)
+    excl[1] = np.zeros(0, np.uint32)                          # a user without exclusions
+    ep = np.zeros(len(users) + 1, np.uint64)
+    ep[1:] = np.cumsum([len(x) for x in excl])
+    ei = np.concatenate(excl).astype(np.uint32)
+    o_items, o_scores = s.topn(users, ep, ei, topn)
+    with make_engine(s) as e:
+        util.push_state(e, s)
+        items, scores = e.topn(users, ep, ei, topn)
+        assert e.stats()["kernel_launches"] > 0
+    _check_topn(items, scores.astype(np.float64), o_items, o_scores, m, topn)
+    # excluded items never appear with a positive score
+    for a in range(len(users)):
+        hit = np.isin(items[a], excl[a]) & (items[a] != 0xFFFFFFFF)
+        assert (scores[a][hit] == 0).all()
+
+
+def test_topn_rejects_bad_arguments():
+    d, s = _oracle_case(50, 40, 500, 8, H.HIER, seed=3)
+    with make_engine(s) as e:
+        util.push_state(e, s)
+        ep = np.zeros(2, np.uint64)
+        with pytest.raises(H.HpfError):
+            e.topn(np.array([50], np.uint32), ep, np.zeros(0, np.uint32), 10)   # user out of range
+        with pytest.raises(H.HpfError):
+            e.topn(np.array([1], np.uint32), ep, np.zeros(0, np.uint32), 1000)  # topn too large
+        ep[1] = 1
+        with pytest.raises(H.HpfError):
+            e.topn(np.array([1], np.uint32), ep, np.array([99], np.uint32), 10)  # excluded item >= m
