@@ -27,7 +27,8 @@
 //               a bitwise count-select in registers and compacts.
 // Keys are 64 bit, (score bits << 32) | ~item: scores are >= 0 so the float bits
 // order like the values, all keys are distinct, and "larger key" is exactly
-// "higher score, ties by lower item" -- the order of oracle/hpf_oracle.c.
+// "higher score, ties by lower item" (the reference's qsort is unstable on ties;
+// this repo fixes them by ascending item, as its parity tests do).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>

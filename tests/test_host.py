@@ -1,0 +1,81 @@
+"""Host-side logic of the C++ driver (hgaprec_b200/host) against the reference's own
+dumps -- no GPU involved.  tests/golden/ref_*.npz were written by the unmodified
+reference behind oracle/ref_harness.cc: the CSR as the reference walks it, its id
+maps, its held-out maps and the state right after HGAPRec::initialize().  The
+driver's reader + CSR builder + start state must reproduce them from the same TSVs."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from oracle import hpf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "hgaprec_b200", "host")
+CHECK = os.path.join(ROOT, "hgaprec_b200", "bin", "hgaprec_hostcheck")
+
+SWITCHES = {
+    "hier": ["-hier"], "hier_bias": ["-hier", "-bias"], "hier_binary": ["-hier", "-binary-data", "-rating-threshold", "3"],
+    "bpf": [], "bpf_bias": ["-bias"], "bpf_bias_novb": ["-bias", "-novb"],
+}
+
+
+@pytest.fixture(scope="module")
+def hostcheck():
+    subprocess.check_call(["make", "-C", HOST, "../bin/hgaprec_hostcheck"], stdout=subprocess.DEVNULL)
+    return CHECK
+
+
+@pytest.mark.parametrize("mode", util.MODES)
+def test_reader_csr_and_start_state_match_reference(hostcheck, tmp_path, mode):
+    g = util.load_golden(mode)
+    n, m, k = (int(v) for v in g["T0/meta"][:3])
+    data = str(tmp_path / "data")
+    util.write_dataset(g, data, lift=3 if "binary" in mode else 0)
+    out = str(tmp_path / "dump.bin")
+    subprocess.check_call([hostcheck, "-dir", data, "-n", str(n), "-m", str(m), "-k", str(k), "-seed", "777",
+                           "-out", out] + SWITCHES[mode])
+    d = O.read_dump(out)
+    # integer work: bit exact
+    for key in ("csr.row_ptr", "csr.col_idx", "seq2user", "seq2movie", "validation.u", "validation.i", "validation.y",
+                "test.u", "test.i", "test.y"):
+        np.testing.assert_array_equal(d[key], g[key], err_msg=key)
+    if "binary" not in mode:
+        np.testing.assert_array_equal(d["csr.y"], g["csr.y"])
+    else:
+        assert (d["csr.y"] == 1).all()
+    # start state: same mt19937 stream, fp64; psi implementations differ by rounding only
+    want = util.golden_state(g, 0)
+    got = O.state_from_dump(dict(d, meta=g["T0/meta"]))
+    for gname in util.groups(want):
+        for f in ("shape", "rate", "Ev"):
+            np.testing.assert_allclose(got.p[gname][f], want.p[gname][f], rtol=1e-14, atol=0, err_msg="%s.%s" % (gname, f))
+        np.testing.assert_allclose(got.p[gname]["Elogv"], want.p[gname]["Elogv"], rtol=0, atol=2e-13, err_msg=gname)
+
+
+def test_reader_edge_cases(hostcheck, tmp_path):
+    """Capacity limits, duplicate lines, zero ratings and uint8 wrap (src/ratings.cc:63-119,
+    src/env.hh:20), checked against hand-derived expectations of the reference's rules."""
+    data = str(tmp_path / "d")
+    os.makedirs(data)
+    lines = ["10\t100\t5", "10\t101\t0",      # rating 0: dropped, item 101 gets no seq here
+             "10\t102\t3", "11\t100\t4",
+             "10\t102\t1",                     # duplicate (10,102): walked twice, carries the LAST value
+             "12\t103\t2",                     # third user: over -n 2 -> dropped
+             "11\t104\t2",                     # third item: over -m 2 -> dropped
+             "11\t102\t260"]                   # 260 wraps to 4 in a uint8
+    open(os.path.join(data, "train.tsv"), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(data, "validation.tsv"), "w").write("10\t100\t2\n12\t100\t1\n11\t102\t0\n")
+    open(os.path.join(data, "test.tsv"), "w").write("11\t100\t5\n11\t100\t1\n")   # same pair twice: last wins
+    out = str(tmp_path / "o.bin")
+    subprocess.check_call([hostcheck, "-dir", data, "-n", "2", "-m", "2", "-k", "3", "-hier", "-out", out])
+    d = O.read_dump(out)
+    np.testing.assert_array_equal(d["seq2user"], [10, 11])
+    np.testing.assert_array_equal(d["seq2movie"], [100, 102])
+    np.testing.assert_array_equal(d["csr.row_ptr"], [0, 3, 5])
+    np.testing.assert_array_equal(d["csr.col_idx"], [0, 1, 1, 0, 1])
+    np.testing.assert_array_equal(d["csr.y"], [5, 1, 1, 4, 4])
+    np.testing.assert_array_equal(d["validation.u"], [0])
+    np.testing.assert_array_equal(d["test.y"], [1])

@@ -87,3 +87,26 @@ def compare_states(got, want, rel=TOL_REL_1IT, elog_abs=TOL_ELOG_ABS_1IT):
         if not d <= elog_abs:
             bad.append("%s.Elogv max abs %.3g > %.3g" % (gname, d, elog_abs))
     return bad
+
+
+def write_dataset(g, path, extra_lines=(), lift=0):
+    """TSVs that reproduce the golden's CSR: users in seq order, rows in walk order.
+    `lift` raises every rating to at least that value (the -binary-data goldens hold
+    the 1s the reference stored, the file must pass its -rating-threshold)."""
+    os.makedirs(path, exist_ok=True)
+    uid, iid = g["seq2user"], g["seq2movie"]
+    rp = g["csr.row_ptr"].astype(np.int64)
+    with open(os.path.join(path, "train.tsv"), "w") as f:
+        for u in range(len(rp) - 1):
+            for j in range(rp[u], rp[u + 1]):
+                f.write("%d\t%d\t%d\n" % (uid[u], iid[g["csr.col_idx"][j]], max(int(g["csr.y"][j]), lift)))
+        for line in extra_lines:
+            f.write(line)
+    for split in ("validation", "test"):
+        with open(os.path.join(path, split + ".tsv"), "w") as f:
+            for u, i, y in zip(g[split + ".u"], g[split + ".i"], g[split + ".y"]):
+                f.write("%d\t%d\t%d\n" % (uid[u], iid[i], max(int(y), lift)))
+            f.write("%d\t%d\t%d\n" % (uid[0], 987654, 3))   # item never seen in training: dropped (ratings.cc:79-81)
+    with open(os.path.join(path, "test_users.tsv"), "w") as f:
+        for u in sorted(set(g["test.u"].tolist())):
+            f.write("%d\n" % uid[u])
