@@ -82,6 +82,7 @@ def load_library():
     L.hpf_iterate.argtypes = [vp, u32]
     L.hpf_heldout_loglik.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_double)]
     L.hpf_topn.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
+    L.hpf_partition_users.argtypes = [vp, u32, u32, vp]
     L.hpf_comm_unique_id.argtypes = [vp, ctypes.c_size_t]
     L.hpf_comm_init.argtypes = [vp, cint, cint, vp, ctypes.c_size_t]
     L.hpf_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
@@ -96,6 +97,17 @@ def _p(a):
 
 def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def partition_users(row_ptr, nranks):
+    """hpf_partition_users: nranks + 1 user bounds, contiguous ranges balanced by nonzeros."""
+    L = load_library()
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    out = np.zeros(nranks + 1, dtype=np.uint32)
+    rc = L.hpf_partition_users(_p(rp), len(rp) - 1, int(nranks), _p(out))
+    if rc != 0:
+        raise HpfError(rc, L.hpf_last_error(None).decode())
+    return out
 
 
 def comm_unique_id():

@@ -1088,6 +1088,21 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
   return 0;
 }
 
+int hpf_partition_users(const uint64_t *row_ptr, uint32_t n_users, uint32_t nranks, uint32_t *first)
+{
+  if (!row_ptr || !first || nranks == 0) return fail(nullptr, HPF_EINVAL, "bad partition arguments");
+  const uint64_t nnz = row_ptr[n_users];
+  first[0] = 0;
+  for (uint32_t r = 1; r < nranks; ++r) {
+    // smallest u whose prefix holds at least r/nranks of the nonzeros, never before the previous cut
+    const uint64_t want = (uint64_t)(((unsigned __int128)nnz * r) / nranks);
+    const uint64_t *p = std::lower_bound(row_ptr + first[r - 1], row_ptr + n_users + 1, want);
+    first[r] = (uint32_t)std::min<uint64_t>((uint64_t)(p - row_ptr), n_users);
+  }
+  first[nranks] = n_users;
+  return 0;
+}
+
 int hpf_comm_unique_id(void *id_out, size_t id_bytes)
 {
   std::string err;

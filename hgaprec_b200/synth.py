@@ -32,8 +32,12 @@ def make_ratings(n, m, nnz, binary=False, seed=0, zipf_s=1.0, sigma=1.0, heldout
                  device=None, users_lo=0, users_hi=None):
     """Return dict(n, m, row_ptr, col_idx, y, heldout=(u, i, y) or None).
 
-    users_lo/users_hi select a contiguous user range of the SAME global data set
-    (used to build one rank's shard without materialising the others)."""
+    users_lo/users_hi generate only a contiguous user range of an n-user problem
+    (one rank's shard, without materialising the others): same item popularity,
+    same activity law and per-user rates as the global problem, but the draws of a
+    range are its own -- the ranges of different calls are statistically alike,
+    they do not tile one fixed data set.  Tests that need exact shards slice a
+    full CSR with hpf_partition_users instead."""
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
     dev = torch.device(device)

@@ -160,6 +160,14 @@ HPF_API int hpf_topn(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
  * the other ranks by any means (bench.py uses torch.distributed).  After this,
  * hpf_iterate all-reduces the item-side accumulators once per iteration and
  * hpf_heldout_loglik stays rank-local. */
+/* Contiguous user ranges balanced by NONZEROS (not by user count) for nranks
+ * shards: first_user_out[r] .. first_user_out[r+1] is rank r's range
+ * (nranks + 1 entries, first 0, last n_users).  Pure host arithmetic on the CSR
+ * row pointer; needs no device and no ctx.  The reference has no counterpart
+ * (it is single-threaded); this is the partition of SURVEY.md 8e. */
+HPF_API int hpf_partition_users(const uint64_t *row_ptr, uint32_t n_users, uint32_t nranks,
+                        uint32_t *first_user_out);
+
 #define HPF_COMM_ID_BYTES 128
 HPF_API int hpf_comm_unique_id(void *id_out, size_t id_bytes);
 HPF_API int hpf_comm_init(hpf_ctx *ctx, int rank, int nranks, const void *id, size_t id_bytes);

@@ -1,0 +1,168 @@
+"""N > 1: users are sharded over ranks (contiguous ranges balanced by nonzeros),
+the item side is replicated and one all-reduce per iteration sums the item-side
+block.  CPU part: the partition arithmetic and the world_size-2
+plumbing over gloo.  GPU part (needs two devices; run with `gpurun --gpus 2`): two
+engines, one per GPU, joined by NCCL, against the single-GPU engine and the oracle."""
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+import util
+import hgaprec_b200 as H
+from hgaprec_b200 import synth
+from oracle import hpf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ CPU
+def test_partition_is_contiguous_and_balanced_by_nonzeros():
+    rng = np.random.default_rng(0)
+    deg = np.concatenate([rng.integers(0, 5, 1000), [5000], rng.integers(0, 50, 3000), np.zeros(40, np.int64)])
+    rp = np.zeros(len(deg) + 1, np.uint64)
+    rp[1:] = np.cumsum(deg)
+    for nr in (1, 2, 3, 4, 8):
+        b = H.partition_users(rp, nr)
+        assert b[0] == 0 and b[-1] == len(deg) and (np.diff(b.astype(np.int64)) >= 0).all()
+        per = np.diff(rp[b].astype(np.int64))
+        # no shard exceeds its fair share by more than the heaviest single user
+        assert per.max() <= rp[-1] / nr + deg.max()
+        assert per.sum() == rp[-1]
+    # degenerate inputs: more ranks than users, no ratings at all
+    b = H.partition_users(np.array([0, 3, 4], np.uint64), 5)
+    assert b[0] == 0 and b[-1] == 2 and (np.diff(b.astype(np.int64)) >= 0).all()
+    b = H.partition_users(np.zeros(4, np.uint64), 2)
+    assert b[0] == 0 and b[-1] == 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank cuts ITS shard out of the same seeded data set with the library's partition
+        n, m, nnz = 4000, 300, 60000
+        full = synth.make_ratings(n, m, nnz, seed=99, device="cpu")
+        bounds = H.partition_users(full["row_ptr"], world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        frp = full["row_ptr"].astype(np.int64)
+        mine = dict(row_ptr=(frp[lo:hi + 1] - frp[lo]).astype(np.uint64), col_idx=full["col_idx"][frp[lo]:frp[hi]],
+                    y=full["y"][frp[lo]:frp[hi]])
+        # what bench.py does: the engine id travels by broadcast_object_list, timings by all_reduce(MAX)
+        obj = [bytes(range(128)) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        import torch
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([float(len(mine["col_idx"]))], dtype=torch.float64)
+        dist.all_reduce(cnt)
+        # the ranks' shards tile the global CSR: gather the pieces on every rank and compare
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, hi, mine["col_idx"], mine["y"]))
+        parts.sort(key=lambda p: p[0])
+        ok = (parts[0][0] == 0 and parts[-1][1] == n and all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and
+              np.array_equal(np.concatenate([p[2] for p in parts]), full["col_idx"]) and
+              np.array_equal(np.concatenate([p[3] for p in parts]), full["y"]) and int(mine["row_ptr"][-1]) == len(mine["col_idx"]))
+        q.put((rank, ok, obj[0] == bytes(range(128)), float(t.item()), float(cnt.item()), len(full["col_idx"])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_plumbing_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, shard_ok, id_ok, tmax, total, nnz in res:
+        assert shard_ok and id_ok, res        # shards tile the global CSR exactly; the id arrived intact
+        assert tmax == 2.0 and total == nnz   # MAX over ranks; every nonzero owned by exactly one rank
+
+
+# ------------------------------------------------------------------ GPU (2 devices)
+def _two_gpus():
+    try:
+        import torch
+        return torch.cuda.is_available() and torch.cuda.device_count() >= 2
+    except Exception:
+        return False
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [H.HIER, H.HIER | H.BIAS, H.BIAS, H.BIAS | H.JACOBI])
+def test_two_gpu_shards_match_single_gpu_and_oracle(flags):
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 5000, 1200, 200000, 100, 3
+    d = synth.make_ratings(n, m, nnz, seed=23, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(24)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8)
+    bounds = H.partition_users(d["row_ptr"], 2)
+    rp = d["row_ptr"].astype(np.int64)
+    uid = H.comm_unique_id()
+    out, errs = [None, None], []
+
+    def worker(r):
+        try:
+            lo, hi = int(bounds[r]), int(bounds[r + 1])
+            users = np.arange(lo, hi)
+            with H.Engine(hi - lo, m, k, flags=flags, device=r, n_users_global=n) as e:
+                e.comm_init(r, 2, uid)
+                e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], d["y"][rp[lo]:rp[hi]])
+                util.push_state(e, s, users=users)
+                e.iterate(iters)
+                hu, hi_, hy = d["heldout"]
+                sel = (hu >= lo) & (hu < hi)
+                ll = e.heldout_loglik(hu[sel] - lo, hi_[sel], hy[sel])
+                got = {g: e.get_state(util._IDS[g]) for g in util.groups(s)}
+                out[r] = (got, ll, e.stats())
+        except Exception as ex:  # surfaced in the main thread
+            errs.append(ex)
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    # stitch the shards back together
+    got = O.OracleState(n, m, k, flags)
+    for g in util.groups(s):
+        for f in O.FIELDS:
+            if g.startswith("beta"):
+                np.testing.assert_array_equal(out[0][0][g][f], out[1][0][g][f])  # replicas stay bitwise identical
+                got.p[g][f][...] = out[0][0][g][f].reshape(got.p[g][f].shape)
+            elif g == "theta" and f == "rate" and not (flags & H.HIER):
+                np.testing.assert_array_equal(out[0][0][g][f], out[1][0][g][f])
+                got.p[g][f][...] = out[0][0][g][f]
+            else:
+                got.p[g][f][...] = np.concatenate([out[0][0][g][f], out[1][0][g][f]]).reshape(got.p[g][f].shape)
+    bad = util.compare_states(got, want, rel=6e-5, elog_abs=6e-5)
+    assert not bad, bad
+    hu, hi_, hy = d["heldout"]
+    assert abs((out[0][1] + out[1][1]) - want.heldout(hu, hi_, hy)) / len(hu) <= 2e-4
+    # and against the single-GPU engine: identical up to fp32 summation order (SURVEY.md 8e gate: 1e-5)
+    with H.Engine(n, m, k, flags=flags, device=0) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(iters)
+        one = util.pull_state(e, s)
+    bad = util.compare_states(got, one, rel=1e-5, elog_abs=1e-5)
+    assert not bad, bad
