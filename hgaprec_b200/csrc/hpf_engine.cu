@@ -26,6 +26,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -39,6 +40,22 @@ using namespace hpf;
 namespace {
 
 thread_local std::string g_create_error = "";
+
+// HPF_TRACE=1: wall-clock milliseconds of the set-up phases on stderr (debug aid)
+struct Trace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(cudaStream_t s) : on(getenv("HPF_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hpf trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 // ---- NCCL through dlopen: single-GPU users never need the library ----------
 typedef struct ncclComm *ncclComm_t;
@@ -73,6 +90,22 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// grow-only scratch (device memory or pinned host memory), carved linearly per call
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, off = 0;
+  bool pinned_host = false;
+  void reset() { off = 0; }
+  template <class T> T *get(size_t count)
+  {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) return nullptr;
+    T *p = reinterpret_cast<T *>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
 struct WorkList {       // segments of one orientation, sorted by descending length
   uint4 *seg = nullptr;
   uint32_t *seg_out = nullptr;
@@ -80,6 +113,7 @@ struct WorkList {       // segments of one orientation, sorted by descending len
   uint32_t *multi_row = nullptr, *multi_first = nullptr, *multi_cnt = nullptr;
   const uint32_t *idx = nullptr; // device, per nonzero
   const uint8_t *y = nullptr;
+  size_t seg_cap = 0, seg_out_cap = 0, multi_cap[3] = { 0, 0, 0 };
 };
 
 struct Side {
@@ -94,7 +128,7 @@ struct Side {
   float *colsum_partial = nullptr; // [update_grid x Kp]
   uint32_t *direct_flag = nullptr;
   uint32_t update_grid = 0;
-  size_t part_rows_cap = 0;
+  size_t tpart_cap = 0, tbpart_cap = 0;
   WorkList wl;
   double prior_shape = 0.3, prior_rate = 0.3, pr_prior_shape = 0.3, pr_prior_rate = 0.3;
   double bias_prior_shape = 0.3, bias_prior_rate = 0.3;
@@ -120,6 +154,8 @@ struct hpf_ctx {
   uint64_t nnz = 0;
   uint32_t *csr_idx = nullptr, *csc_idx = nullptr, *upass_idx = nullptr; // upass_*: CSR regrouped by item tile (or null)
   uint8_t *csr_y = nullptr, *csc_y = nullptr, *upass_y = nullptr;
+  size_t csr_idx_cap = 0, csr_y_cap = 0, csc_idx_cap = 0, csc_y_cap = 0, upass_idx_cap = 0, upass_y_cap = 0;
+  Arena dev_arena, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   uint32_t th_tiles = 1, be_tiles = 1;
   uint64_t l2_tile_bytes = 32ull << 20; // factor rows of one gather tile (0: no tiling)
   uint32_t *scratch_u32 = nullptr;
@@ -354,6 +390,70 @@ int refresh_colsum(hpf_ctx *c, Side &s)
   return 0;
 }
 
+// ---- set-up memory: grow-only arenas, so a repeated hpf_set_ratings_csr allocates nothing ----
+// (cudaMalloc / cudaFree synchronise the device and cost milliseconds at GB sizes)
+int arena_reserve(hpf_ctx *c, Arena &a, size_t bytes)
+{
+  a.reset();
+  if (a.cap >= bytes) return 0;
+  bytes += bytes / 8 + (1u << 20);
+  if (a.base) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (a.pinned_host) cudaFreeHost(a.base); else { cudaFree(a.base); c->device_bytes -= a.cap; }
+    a.base = nullptr; a.cap = 0;
+  }
+  void *q = nullptr;
+  if (a.pinned_host) CU(cudaMallocHost(&q, bytes));
+  else { CU(cudaMalloc(&q, bytes)); c->device_bytes += bytes; }
+  a.base = (char *)q; a.cap = bytes;
+  return 0;
+}
+
+template <class T> int ensure(hpf_ctx *c, T **p, size_t *cap, size_t count)
+{
+  if (*p != nullptr && *cap >= count) return 0;
+  dfree(c, *p);
+  *p = nullptr; *cap = 0;
+  const size_t want = count + count / 16 + 64;
+  TRY(dalloc(c, p, want, false));
+  *cap = want;
+  return 0;
+}
+
+size_t pad256(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+int bits_for(uint64_t nvalues)
+{
+  int b = 1;
+  while (b < 32 && (1ull << b) < nvalues) ++b;
+  return b;
+}
+
+// how many tiles the gathered side (C rows of ld floats) is cut into
+uint32_t tiles_for(const hpf_ctx *c, uint32_t C, uint32_t R)
+{
+  if (c->l2_tile_bytes == 0) return 1;
+  const uint64_t bytes = (uint64_t)C * c->ld * sizeof(float);
+  if (bytes <= 2 * c->l2_tile_bytes) return 1;
+  uint64_t t = (bytes + c->l2_tile_bytes - 1) / c->l2_tile_bytes;
+  while (t > 1 && t * (uint64_t)R >= 0xfffffff0ull) --t; // the composite key is 32 bits
+  return (uint32_t)std::min<uint64_t>(t, C);
+}
+
+// scratch device memory of one call (hpf_topn); freed on scope exit
+struct Scratch {
+  std::vector<void *> v;
+  ~Scratch() { for (void *p : v) cudaFree(p); }
+  template <class T> cudaError_t get(T **p, size_t count)
+  {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
+    if (e == cudaSuccess) v.push_back(q);
+    *p = (T *)q;
+    return e;
+  }
+};
+
 // ---- work lists ---------------------------------------------------------------
 // The nonzeros of one orientation arrive as RUNS: run (t, r) holds the nonzeros
 // of row r whose gathered-side index lies in tile t, ptr[t * R + r] is where it
@@ -365,13 +465,22 @@ int refresh_colsum(hpf_ctx *c, Side &s)
 // factor rows -- and, inside a tile, counting-sorted by descending length so
 // that (a) the 32/G segments a warp advances in lock-step have equal trip counts
 // and (b) long work is scheduled first.
-int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, uint32_t ntiles, const uint32_t *d_idx, const uint8_t *d_y)
+struct HostWorkList { // lives in the pinned host arena until uploaded
+  uint4 *seg = nullptr;
+  uint32_t *seg_out = nullptr, *multi_row = nullptr, *multi_first = nullptr, *multi_cnt = nullptr;
+  uint32_t nsegs = 0, nslots = 0, nmulti = 0;
+};
+
+// upper bound of the pinned bytes build_worklist_host carves for one orientation
+size_t worklist_host_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L)
 {
-  WorkList &w = s.wl;
-  dfree(c, w.seg); dfree(c, w.seg_out); dfree(c, w.multi_row); dfree(c, w.multi_first); dfree(c, w.multi_cnt);
-  w = WorkList();
-  w.idx = d_idx; w.y = d_y;
-  const uint32_t R = s.R, L = c->seg_len;
+  const uint64_t segs = nnz / L + (uint64_t)ntiles * R + R + 16;
+  return pad256(segs * sizeof(uint4)) + pad256(segs * 4) + 3 * pad256((size_t)R * 4) + 4096;
+}
+
+int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr, uint32_t ntiles, HostWorkList *out)
+{
+  const uint32_t L = c->seg_len;
   std::vector<uint32_t> segcnt(R, 0);
   for (uint32_t t = 0; t < ntiles; ++t) {
     const uint64_t *pt = ptr + (size_t)t * R;
@@ -381,19 +490,30 @@ int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, uint32_t ntiles, co
     }
   }
   uint64_t nsegs64 = 0;
-  for (uint32_t r = 0; r < R; ++r) nsegs64 += segcnt[r] ? segcnt[r] : 1;
+  uint32_t nmulti = 0;
+  for (uint32_t r = 0; r < R; ++r) {
+    nsegs64 += segcnt[r] ? segcnt[r] : 1;
+    nmulti += segcnt[r] > 1;
+  }
   if (nsegs64 >= 0xfffffff0ull) return fail(c, HPF_EINVAL, "too many work segments (%llu)", (unsigned long long)nsegs64);
   const uint32_t nsegs = (uint32_t)nsegs64;
-  std::vector<uint32_t> multi_row, multi_first, multi_cnt, first(R, 0), next(R, 0);
-  uint32_t nslots = 0;
+  HostWorkList w;
+  w.seg = pin.get<uint4>(nsegs);
+  w.seg_out = pin.get<uint32_t>(nsegs);
+  w.multi_row = pin.get<uint32_t>(nmulti);
+  w.multi_first = pin.get<uint32_t>(nmulti);
+  w.multi_cnt = pin.get<uint32_t>(nmulti);
+  if (!w.seg || !w.seg_out || !w.multi_row || !w.multi_first || !w.multi_cnt)
+    return fail(c, HPF_ENOMEM, "pinned work-list arena too small");
+  std::vector<uint32_t> first(R, 0), next(R, 0);
+  uint32_t nslots = 0, mi = 0;
   for (uint32_t r = 0; r < R; ++r)
     if (segcnt[r] > 1) {
-      multi_row.push_back(r); multi_first.push_back(nslots); multi_cnt.push_back(segcnt[r]);
+      w.multi_row[mi] = r; w.multi_first[mi] = nslots; w.multi_cnt[mi] = segcnt[r];
+      ++mi;
       first[r] = nslots;
       nslots += segcnt[r];
     }
-  std::vector<uint4> seg(nsegs);
-  std::vector<uint32_t> seg_out(nsegs);
   std::vector<uint32_t> bucket(L + 2);
   uint32_t base = 0;
   for (uint32_t t = 0; t < ntiles; ++t) {
@@ -416,8 +536,8 @@ int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, uint32_t ntiles, co
       if (len == 0) {
         if (t == 0 && segcnt[r] == 0) {
           const uint32_t pos = base + bucket[L]++;
-          seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, 0u);
-          seg_out[pos] = r;
+          w.seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, 0u);
+          w.seg_out[pos] = r;
         }
         continue;
       }
@@ -426,119 +546,104 @@ int build_worklist(hpf_ctx *c, Side &s, const uint64_t *ptr, uint32_t ntiles, co
         const uint64_t sb = b0 + (uint64_t)q * L;
         const uint32_t sl = (uint32_t)std::min<uint64_t>(L, len - (uint64_t)q * L);
         const uint32_t pos = base + bucket[L - sl]++;
-        seg[pos] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
-        seg_out[pos] = segcnt[r] == 1 ? r : R + first[r] + next[r]++;
+        w.seg[pos] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
+        w.seg_out[pos] = segcnt[r] == 1 ? r : R + first[r] + next[r]++;
       }
     }
     base += tile_segs;
   }
-  w.nsegs = nsegs; w.npartial = nslots; w.nmulti = (uint32_t)multi_row.size();
-  TRY(dalloc(c, &w.seg, nsegs, false));
-  TRY(dalloc(c, &w.seg_out, nsegs, false));
-  CU(cudaMemcpyAsync(w.seg, seg.data(), sizeof(uint4) * nsegs, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(w.seg_out, seg_out.data(), sizeof(uint32_t) * nsegs, cudaMemcpyHostToDevice, c->stream));
-  if (w.nmulti) {
-    TRY(dalloc(c, &w.multi_row, w.nmulti, false));
-    TRY(dalloc(c, &w.multi_first, w.nmulti, false));
-    TRY(dalloc(c, &w.multi_cnt, w.nmulti, false));
-    CU(cudaMemcpyAsync(w.multi_row, multi_row.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(w.multi_first, multi_first.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(w.multi_cnt, multi_cnt.data(), 4 * w.nmulti, cudaMemcpyHostToDevice, c->stream));
-  }
-  if (nslots > s.part_rows_cap) {
-    dfree(c, s.Tpart); dfree(c, s.Tbpart);
-    s.Tpart = nullptr; s.Tbpart = nullptr;
-    TRY(dalloc(c, &s.Tpart, (size_t)nslots * c->ld, false));
-    if (c->bias) TRY(dalloc(c, &s.Tbpart, nslots, false));
-    s.part_rows_cap = nslots;
-  }
-  CU(cudaStreamSynchronize(c->stream)); // host vectors go out of scope
+  w.nsegs = nsegs; w.nslots = nslots; w.nmulti = nmulti;
+  *out = w;
   return 0;
 }
 
-// scratch device memory of one set-up call
-struct Scratch {
-  std::vector<void *> v;
-  ~Scratch() { for (void *p : v) cudaFree(p); }
-  template <class T> cudaError_t get(T **p, size_t count)
-  {
-    void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16));
-    if (e == cudaSuccess) v.push_back(q);
-    *p = (T *)q;
-    return e;
+// pinned host work list -> the side's device work list (async on the ctx stream)
+int upload_worklist(hpf_ctx *c, Side &s, const HostWorkList &h, const uint32_t *d_idx, const uint8_t *d_y)
+{
+  WorkList &w = s.wl;
+  w.idx = d_idx; w.y = d_y;
+  TRY(ensure(c, &w.seg, &w.seg_cap, h.nsegs));
+  TRY(ensure(c, &w.seg_out, &w.seg_out_cap, h.nsegs));
+  TRY(ensure(c, &w.multi_row, &w.multi_cap[0], h.nmulti));
+  TRY(ensure(c, &w.multi_first, &w.multi_cap[1], h.nmulti));
+  TRY(ensure(c, &w.multi_cnt, &w.multi_cap[2], h.nmulti));
+  w.nsegs = h.nsegs; w.npartial = h.nslots; w.nmulti = h.nmulti;
+  CU(cudaMemcpyAsync(w.seg, h.seg, sizeof(uint4) * h.nsegs, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(w.seg_out, h.seg_out, 4 * (size_t)h.nsegs, cudaMemcpyHostToDevice, c->stream));
+  if (h.nmulti) {
+    CU(cudaMemcpyAsync(w.multi_row, h.multi_row, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(w.multi_first, h.multi_first, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(w.multi_cnt, h.multi_cnt, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
   }
+  TRY(ensure(c, &s.Tpart, &s.tpart_cap, (size_t)h.nslots * c->ld));
+  if (c->bias) TRY(ensure(c, &s.Tbpart, &s.tbpart_cap, h.nslots));
+  return 0;
+}
+
+// Device half of one orientation: order the nonzeros by (tile of col, row) -- the
+// gathered-side index and the rating permuted accordingly -- and leave the run
+// pointers in pinned host memory (async).  d_row / d_col / d_y are per nonzero in
+// the caller's CSR order.  presorted: the input is already ordered by row.
+struct Orientation {
+  uint32_t ntiles = 1, tile_cols = 0;
+  bool from_host_rowptr = false; // presorted and one tile: the CSR itself, nothing to do on the device
+  uint64_t *h_run = nullptr;     // pinned, ntiles * R + 1
+  const uint32_t *d_idx = nullptr;
+  const uint8_t *d_y = nullptr;
 };
 
-int bits_for(uint64_t nvalues)
+size_t orientation_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, size_t cub_bytes)
 {
-  int b = 1;
-  while (b < 32 && (1ull << b) < nvalues) ++b;
-  return b;
+  return 4 * pad256(nnz * 4) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
 }
 
-// how many tiles the gathered side (C rows of ld floats) is cut into
-uint32_t tiles_for(const hpf_ctx *c, uint32_t C, uint32_t R)
-{
-  if (c->l2_tile_bytes == 0) return 1;
-  const uint64_t bytes = (uint64_t)C * c->ld * sizeof(float);
-  if (bytes <= 2 * c->l2_tile_bytes) return 1;
-  uint64_t t = (bytes + c->l2_tile_bytes - 1) / c->l2_tile_bytes;
-  while (t > 1 && t * (uint64_t)R >= 0xfffffff0ull) --t; // the composite key is 32 bits
-  return (uint32_t)std::min<uint64_t>(t, C);
-}
-
-// One orientation of the ratings: nonzeros ordered by (tile of col, row), with
-// the gathered-side index and the rating permuted accordingly, and its work
-// list.  d_row / d_col / d_y are per nonzero in the caller's CSR order.
-// presorted: the input is already ordered by row (the CSR itself).
-int build_orientation(hpf_ctx *c, Side &s, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y, bool presorted,
-                      uint32_t R, uint32_t C, const uint64_t *host_row_ptr, uint32_t **own_idx, uint8_t **own_y,
-                      uint32_t *ntiles_out)
+int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y,
+                  bool presorted, uint32_t R, uint32_t C, uint32_t **own_idx, size_t *own_idx_cap, uint8_t **own_y,
+                  size_t *own_y_cap, size_t cub_bytes, Orientation *o)
 {
   const uint64_t nnz = c->nnz;
-  const uint32_t ntiles = tiles_for(c, C, R);
-  const uint32_t tile_cols = (uint32_t)(((uint64_t)C + ntiles - 1) / ntiles);
-  *ntiles_out = ntiles;
-  dfree(c, *own_idx); dfree(c, *own_y);
-  *own_idx = nullptr; *own_y = nullptr;
-  if (presorted && ntiles == 1) return build_worklist(c, s, host_row_ptr, 1, d_col, d_y);
-  std::vector<uint64_t> run_ptr((size_t)ntiles * R + 1, 0);
-  if (nnz > 0) {
-    TRY(dalloc(c, own_idx, nnz, false));
-    if (d_y) TRY(dalloc(c, own_y, nnz, false));
-    Scratch tmp;
-    uint32_t *perm = nullptr, *perm2 = nullptr, *key = nullptr, *key2 = nullptr;
-    uint64_t *d_run = nullptr;
-    void *d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nnz, 0, 32, c->stream);
-    CU(tmp.get(&perm, nnz)); CU(tmp.get(&perm2, nnz)); CU(tmp.get(&key, nnz)); CU(tmp.get(&key2, nnz));
-    CU(tmp.get(&d_run, run_ptr.size())); CU(tmp.get((char **)&d_tmp, tmp_bytes));
-    const unsigned nb = (unsigned)((nnz + 255) / 256);
-    iota_kernel<<<nb, 256, 0, c->stream>>>(perm, nnz);
-    c->launches++;
-    if (!presorted) { // stable sort by row
-      CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_row, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0,
-                                         bits_for(R), c->stream));
-      std::swap(perm, perm2);
-    }
-    if (ntiles > 1) { // then stable sort by the tile of the gathered-side index
-      gather_key_kernel<<<nb, 256, 0, c->stream>>>(perm, d_col, tile_cols, nnz, key);
-      c->launches++;
-      CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint32_t *)perm, perm2,
-                                         (int64_t)nnz, 0, bits_for(ntiles), c->stream));
-      std::swap(perm, perm2);
-    }
-    apply_perm_kernel<<<nb, 256, 0, c->stream>>>(perm, d_row, d_col, d_y, tile_cols, R, nnz, *own_idx, *own_y, key);
-    run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key, nnz, ntiles * R, d_run);
-    c->launches += 2;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(run_ptr.data(), d_run, run_ptr.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+  o->ntiles = tiles_for(c, C, R);
+  o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
+  if (presorted && o->ntiles == 1) {
+    o->from_host_rowptr = true;
+    o->d_idx = d_col; o->d_y = d_y;
+    return 0;
   }
-  return build_worklist(c, s, run_ptr.data(), ntiles, *own_idx, *own_y);
+  const size_t nruns = (size_t)o->ntiles * R;
+  o->h_run = pin.get<uint64_t>(nruns + 1);
+  if (!o->h_run) return fail(c, HPF_ENOMEM, "pinned run-pointer arena too small");
+  TRY(ensure(c, own_idx, own_idx_cap, nnz));
+  if (d_y) TRY(ensure(c, own_y, own_y_cap, nnz));
+  o->d_idx = *own_idx; o->d_y = d_y ? *own_y : nullptr;
+  if (nnz == 0) {
+    memset(o->h_run, 0, (nruns + 1) * 8);
+    return 0;
+  }
+  uint32_t *perm = dev.get<uint32_t>(nnz), *perm2 = dev.get<uint32_t>(nnz), *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz);
+  uint64_t *d_run = dev.get<uint64_t>(nruns + 1);
+  void *d_tmp = dev.get<char>(cub_bytes);
+  if (!perm || !perm2 || !key || !key2 || !d_run || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  size_t tmp_bytes = cub_bytes;
+  const unsigned nb = (unsigned)((nnz + 255) / 256);
+  iota_kernel<<<nb, 256, 0, c->stream>>>(perm, nnz);
+  c->launches++;
+  if (!presorted) { // stable sort by row
+    CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_row, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0, bits_for(R), c->stream));
+    std::swap(perm, perm2);
+  }
+  if (o->ntiles > 1) { // then stable sort by the tile of the gathered-side index
+    gather_key_kernel<<<nb, 256, 0, c->stream>>>(perm, d_col, o->tile_cols, nnz, key);
+    c->launches++;
+    CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0,
+                                       bits_for(o->ntiles), c->stream));
+    std::swap(perm, perm2);
+  }
+  apply_perm_kernel<<<nb, 256, 0, c->stream>>>(perm, d_row, d_col, d_y, o->tile_cols, R, nnz, *own_idx, d_y ? *own_y : nullptr, key);
+  run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key, nnz, (uint32_t)nruns, d_run);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(o->h_run, d_run, (nruns + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
 }
 
 int ensure_aux(hpf_ctx *c)
@@ -709,6 +814,8 @@ void hpf_destroy(hpf_ctx *c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto &p : c->allocs) cudaFree(p.first);
+  if (c->dev_arena.base) cudaFree(c->dev_arena.base);
+  if (c->pin_arena.base) cudaFreeHost(c->pin_arena.base);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (auto &e : c->pev) if (e) cudaEventDestroy(e);
@@ -727,37 +834,70 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     if (row_ptr[r + 1] < row_ptr[r]) return fail(c, HPF_EINVAL, "row_ptr not monotone at row %u", r);
   if (nnz > 0 && !col_idx) return fail(c, HPF_EINVAL, "col_idx is null");
   if (nnz >= 0xffffffffull) return fail(c, HPF_EINVAL, "nnz=%llu per ctx exceeds 2^32-1", (unsigned long long)nnz);
+  Trace tr(c->stream);
   c->ratings_set = false;
-  dfree(c, c->csr_idx); dfree(c, c->csr_y);
-  c->csr_idx = nullptr; c->csr_y = nullptr;
   c->nnz = nnz;
-  TRY(dalloc(c, &c->csr_idx, nnz, false));
-  if (y) TRY(dalloc(c, &c->csr_y, nnz, false));
-  Scratch tmp;
-  uint64_t *d_rowptr = nullptr;
-  uint32_t *d_rowof = nullptr;
+  c->pin_arena.pinned_host = true;
+  const uint32_t th_t = tiles_for(c, m, n), be_t = tiles_for(c, n, m);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int64_t)std::max<uint64_t>(nnz, 1), 0, 32, c->stream);
+  // the two orientations are built one after the other on the stream, so they share the device scratch
+  const size_t dev_need = pad256(((size_t)n + 1) * 8) + pad256(nnz * 4) +
+                          std::max(orientation_dev_bytes(nnz, n, th_t, cub_bytes), orientation_dev_bytes(nnz, m, be_t, cub_bytes));
+  const size_t pin_need = pad256(((size_t)th_t * n + 1) * 8) + pad256(((size_t)be_t * m + 1) * 8) +
+                          worklist_host_bytes(nnz, n, th_t, c->seg_len) + worklist_host_bytes(nnz, m, be_t, c->seg_len);
+  TRY(arena_reserve(c, c->dev_arena, dev_need));
+  TRY(arena_reserve(c, c->pin_arena, pin_need));
+  TRY(ensure(c, &c->csr_idx, &c->csr_idx_cap, nnz));
+  if (y) TRY(ensure(c, &c->csr_y, &c->csr_y_cap, nnz));
+  const uint8_t *d_y = y ? c->csr_y : nullptr;
+  tr.mark("reserve");
+
+  // ---- device half, all asynchronous: upload, argument check, both orderings
+  uint64_t *d_rowptr = c->dev_arena.get<uint64_t>((size_t)n + 1);
+  uint32_t *d_rowof = c->dev_arena.get<uint32_t>(nnz);
+  if (!d_rowptr || !d_rowof) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  Orientation uo, io;
+  CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
   if (nnz > 0) {
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
-    CU(tmp.get(&d_rowptr, (size_t)n + 1)); CU(tmp.get(&d_rowof, nnz));
     CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     const unsigned nb = (unsigned)((nnz + 255) / 256);
-    // argument check on the device: every item index must be < n_items
-    CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
-    check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32);
+    check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32); // every item index must be < n_items
     expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
     c->launches += 2;
-    uint32_t bad = 0;
-    CU(cudaMemcpyAsync(&bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", bad, m);
   }
-  // user pass: rows = users (the CSR order itself), gathers item rows
-  TRY(build_orientation(c, c->th, d_rowof, c->csr_idx, c->csr_y, true, n, m, row_ptr, &c->upass_idx, &c->upass_y,
-                        &c->th_tiles));
+  uint32_t *h_bad = c->pin_arena.get<uint32_t>(1);
+  if (!h_bad) return fail(c, HPF_ENOMEM, "pinned arena too small");
+  *h_bad = 0;
+  CU(cudaMemcpyAsync(h_bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
+  const size_t dev_mark = c->dev_arena.off;
   // item pass: rows = items, gathers user rows; users stay ascending inside a run
-  TRY(build_orientation(c, c->be, c->csr_idx, d_rowof, c->csr_y, false, m, n, nullptr, &c->csc_idx, &c->csc_y,
-                        &c->be_tiles));
+  TRY(orient_device(c, c->dev_arena, c->pin_arena, c->csr_idx, d_rowof, d_y, false, m, n, &c->csc_idx, &c->csc_idx_cap, &c->csc_y,
+                    &c->csc_y_cap, cub_bytes, &io));
+  c->dev_arena.off = dev_mark; // stream order makes the scratch reusable
+  // user pass: rows = users (the CSR order itself), gathers item rows
+  TRY(orient_device(c, c->dev_arena, c->pin_arena, d_rowof, c->csr_idx, d_y, true, n, m, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
+                    &c->upass_y_cap, cub_bytes, &uo));
+  c->th_tiles = uo.ntiles; c->be_tiles = io.ntiles;
+
+  // ---- host half, overlapped with the device: the user-pass work list straight from the caller's row_ptr
+  HostWorkList uw, iw;
+  if (uo.from_host_rowptr) TRY(build_worklist_host(c, c->pin_arena, n, row_ptr, 1, &uw));
+  tr.mark("enqueue + user work list");
+  CU(cudaStreamSynchronize(c->stream));
+  tr.mark("device: upload, sorts");
+  if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
+  if (!uo.from_host_rowptr) TRY(build_worklist_host(c, c->pin_arena, n, uo.h_run, uo.ntiles, &uw));
+  TRY(build_worklist_host(c, c->pin_arena, m, io.h_run, io.ntiles, &iw));
+  tr.mark("item work list");
+  TRY(upload_worklist(c, c->th, uw, uo.d_idx, uo.d_y));
+  TRY(upload_worklist(c, c->be, iw, io.d_idx, io.d_y));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  tr.mark("work-list upload");
   c->ratings_set = true;
   return 0;
 }
@@ -953,12 +1093,12 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   for (uint64_t p = 0; p < npairs; ++p)
     if (u[p] >= c->th.R || i[p] >= c->be.R) return fail(c, HPF_EINVAL, "pair %llu out of range", (unsigned long long)p);
-  uint32_t *du = nullptr, *di = nullptr;
-  uint8_t *dy = nullptr;
-  cudaError_t e = cudaMalloc((void **)&du, npairs * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&di, npairs * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&dy, npairs);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(du, u, npairs * 4, cudaMemcpyHostToDevice, c->stream);
+  // pairs go through the grow-only set-up arena: no allocation in the steady state
+  TRY(arena_reserve(c, c->dev_arena, 2 * pad256(npairs * 4) + pad256(npairs) + 4096));
+  uint32_t *du = c->dev_arena.get<uint32_t>(npairs), *di = c->dev_arena.get<uint32_t>(npairs);
+  uint8_t *dy = c->dev_arena.get<uint8_t>(npairs);
+  if (!du || !di || !dy) return fail(c, HPF_ENOMEM, "device arena too small");
+  cudaError_t e = cudaMemcpyAsync(du, u, npairs * 4, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(di, i, npairs * 4, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, npairs, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
@@ -976,7 +1116,6 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
     e = cudaMemcpyAsync(sum_ll, c->ll_out, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   }
-  cudaFree(du); cudaFree(di); cudaFree(dy);
   if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_heldout_loglik: %s", cudaGetErrorString(e));
   return 0;
 }
