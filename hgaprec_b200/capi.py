@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhpf_b200.so")
+LIB_PATH = os.environ.get("HPF_LIB") or os.path.join(HERE, "libhpf_b200.so")  # HPF_LIB: tuning variants
 CSRC = os.path.join(HERE, "csrc")
 
 ABI_VERSION = 1
@@ -44,12 +44,14 @@ class _Config(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("iterations", ctypes.c_uint64),
                 ("slow_path_nnz", ctypes.c_uint64), ("nnz", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
-                ("last_iterate_ms", ctypes.c_float), ("sweep_group", ctypes.c_uint32), ("sweep_vec", ctypes.c_uint32)]
+                ("last_iterate_ms", ctypes.c_float), ("sweep_group", ctypes.c_uint32), ("sweep_vec", ctypes.c_uint32),
+                ("tile_rows", ctypes.c_uint32), ("item_tiles", ctypes.c_uint32), ("head_nnz", ctypes.c_uint64),
+                ("tile_segments", ctypes.c_uint64)]
 
 
 class IterProfile(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("sweep_user_ms", "sweep_item_ms", "combine_ms", "update_theta_ms",
-                                             "allreduce_ms", "update_beta_ms", "total_ms")]
+                                             "allreduce_ms", "update_beta_ms", "total_ms", "sweep_user_head_ms")]
 
 
 _lib = None

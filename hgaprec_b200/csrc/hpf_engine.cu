@@ -22,6 +22,7 @@
 #include "hpf_topn.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cudaTypedefs.h>
 #include <dlfcn.h>
 
@@ -106,6 +107,18 @@ struct Arena {
   }
 };
 
+struct TilePlan {       // work of one tile_sweep_kernel launch
+  bool on = false;
+  uint4 *seg = nullptr; size_t seg_cap = 0;
+  uint32_t *tile_ptr = nullptr; size_t tile_ptr_cap = 0;
+  uint32_t *idx = nullptr; size_t idx_cap = 0;   // per nonzero: slot inside its tile
+  uint8_t *y = nullptr; size_t y_cap = 0;
+  uint32_t *row_ids = nullptr; size_t row_ids_cap = 0; // explicit rows of a single tile (head items)
+  uint32_t ntiles = 0, cpt = 1, nsegs = 0, tile0_count = 0;
+  uint64_t nnz = 0;
+  bool has_y = false;
+};
+
 struct WorkList {       // segments of one orientation, sorted by descending length
   uint4 *seg = nullptr;
   uint32_t *seg_out = nullptr;
@@ -144,7 +157,7 @@ struct hpf_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t pev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   bool profiling = false;
   std::string err;
   std::vector<std::pair<void *, size_t>> allocs;
@@ -155,7 +168,11 @@ struct hpf_ctx {
   uint32_t *csr_idx = nullptr, *csc_idx = nullptr, *upass_idx = nullptr; // upass_*: CSR regrouped by item tile (or null)
   uint8_t *csr_y = nullptr, *csc_y = nullptr, *upass_y = nullptr;
   size_t csr_idx_cap = 0, csr_y_cap = 0, csc_idx_cap = 0, csc_y_cap = 0, upass_idx_cap = 0, upass_y_cap = 0;
-  Arena dev_arena, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
+  Arena dev_arena, dev_arena2, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
+  TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
+  uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
+  uint32_t tile_rows = 0; size_t tile_smem = 0;
+  int item_tile_mode = 0, head_tile_mode = 0; // 0 off (default: measured slower than the gather kernel), 1 forced, -1 auto
   uint32_t th_tiles = 1, be_tiles = 1;
   uint64_t l2_tile_bytes = 32ull << 20; // factor rows of one gather tile (0: no tiling)
   uint32_t *scratch_u32 = nullptr;
@@ -336,6 +353,62 @@ int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside)
   return fail(c, HPF_EINVAL, "unsupported sweep group %d", c->sweep_g);
 }
 
+template <int G, int V> int launch_tile_gv(hpf_ctx *c, const TileArgs &a, uint32_t grid)
+{
+  if (c->bias) {
+    CU(cudaFuncSetAttribute(tile_sweep_kernel<G, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+    tile_sweep_kernel<G, V, true><<<grid, kTileThreads, c->tile_smem, c->stream>>>(a);
+  } else {
+    CU(cudaFuncSetAttribute(tile_sweep_kernel<G, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+    tile_sweep_kernel<G, V, false><<<grid, kTileThreads, c->tile_smem, c->stream>>>(a);
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <int G> int launch_tile_g(hpf_ctx *c, const TileArgs &a, uint32_t grid)
+{
+  switch (c->sweep_v) {
+  case 1: return launch_tile_gv<G, 1>(c, a, grid);
+  case 2: return launch_tile_gv<G, 2>(c, a, grid);
+  case 3: return launch_tile_gv<G, 3>(c, a, grid);
+  case 4: return launch_tile_gv<G, 4>(c, a, grid);
+  case 5: return launch_tile_gv<G, 5>(c, a, grid);
+  case 6: return launch_tile_gv<G, 6>(c, a, grid);
+  case 7: return launch_tile_gv<G, 7>(c, a, grid);
+  case 8: return launch_tile_gv<G, 8>(c, a, grid);
+  }
+  return fail(c, HPF_EINVAL, "unsupported sweep shape G=%d V=%d", G, c->sweep_v);
+}
+
+// tile sweep of `plan`: rows on `rowside`, tiles of `colside` rows staged in shared memory; adds into rowside.T
+int launch_tile_sweep(hpf_ctx *c, const TilePlan &plan, Side &rowside, Side &colside)
+{
+  if (!plan.on || plan.nsegs == 0) return 0;
+  TileArgs a;
+  memset(&a, 0, sizeof a);
+  a.seg = plan.seg; a.tile_seg_ptr = plan.tile_ptr; a.ntiles = plan.ntiles; a.cpt = plan.cpt;
+  a.tile_rows = c->tile_rows; a.C = colside.R;
+  a.tile_row_ids = plan.tile0_count ? plan.row_ids : nullptr; a.tile0_count = plan.tile0_count;
+  a.idx = plan.idx; a.y = plan.has_y ? plan.y : nullptr;
+  a.Arow = rowside.A; a.Acol = colside.A; a.T = rowside.T;
+  a.row_aux = rowside.aux; a.col_aux = colside.aux; a.Tb = rowside.Tb;
+  a.ElogRow = rowside.Elog; a.ElogCol = colside.Elog; a.ElogbRow = rowside.b_Elog; a.ElogbCol = colside.b_Elog;
+  a.Tdirect = rowside.Tdirect; a.Tbdirect = rowside.Tbdirect; a.direct_flag = rowside.direct_flag; a.slow_count = c->slow_count;
+  a.K = c->K; a.K4 = c->K4; a.ld = c->ld; a.ld4 = c->ld / 4;
+  const uint32_t grid = std::min<uint32_t>(plan.ntiles * plan.cpt, (uint32_t)c->sm_count);
+  switch (c->sweep_g) {
+  case 1: return launch_tile_g<1>(c, a, grid);
+  case 2: return launch_tile_g<2>(c, a, grid);
+  case 4: return launch_tile_g<4>(c, a, grid);
+  case 8: return launch_tile_g<8>(c, a, grid);
+  case 16: return launch_tile_g<16>(c, a, grid);
+  case 32: return launch_tile_g<32>(c, a, grid);
+  }
+  return fail(c, HPF_EINVAL, "unsupported sweep group %d", c->sweep_g);
+}
+
 int launch_combine(hpf_ctx *c, Side &s)
 {
   if (s.wl.nmulti == 0) return 0;
@@ -370,7 +443,7 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   update_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
-  colsum_finalize_kernel<<<(c->Kp + 127) / 128, 128, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
+  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
                                                                      s.direct_flag);
   c->launches++;
   CU(cudaGetLastError());
@@ -383,7 +456,7 @@ int refresh_colsum(hpf_ctx *c, Side &s)
   colsum_partial_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(s.Ev, s.R, c->Kp, c->ld, s.colsum_partial);
   c->launches++;
   CU(cudaGetLastError());
-  colsum_finalize_kernel<<<(c->Kp + 127) / 128, 128, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
+  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
                                                                      nullptr);
   c->launches++;
   CU(cudaGetLastError());
@@ -587,7 +660,8 @@ int upload_worklist(hpf_ctx *c, Side &s, const HostWorkList &h, const uint32_t *
 struct Orientation {
   uint32_t ntiles = 1, tile_cols = 0;
   bool from_host_rowptr = false; // presorted and one tile: the CSR itself, nothing to do on the device
-  uint64_t *h_run = nullptr;     // pinned, ntiles * R + 1
+  uint64_t *h_run = nullptr;     // pinned, ntiles * R + 1 (when asked for)
+  uint64_t *d_run = nullptr;     // the same on the device (set-up arena)
   const uint32_t *d_idx = nullptr;
   const uint8_t *d_y = nullptr;
 };
@@ -597,32 +671,41 @@ size_t orientation_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, size_t c
   return 4 * pad256(nnz * 4) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
 }
 
-int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y,
-                  bool presorted, uint32_t R, uint32_t C, uint32_t **own_idx, size_t *own_idx_cap, uint8_t **own_y,
-                  size_t *own_y_cap, size_t cub_bytes, Orientation *o)
+int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, uint64_t nnz, const uint32_t *d_row, const uint32_t *d_col,
+                  const uint8_t *d_y, bool presorted, uint32_t R, uint32_t C, uint32_t force_tile_cols, bool want_host_run,
+                  uint32_t **own_idx, size_t *own_idx_cap, uint8_t **own_y, size_t *own_y_cap, size_t cub_bytes, Orientation *o)
 {
-  const uint64_t nnz = c->nnz;
-  o->ntiles = tiles_for(c, C, R);
-  o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
+  if (force_tile_cols) {
+    o->tile_cols = force_tile_cols;
+    o->ntiles = (uint32_t)(((uint64_t)C + force_tile_cols - 1) / force_tile_cols);
+  } else {
+    o->ntiles = tiles_for(c, C, R);
+    o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
+  }
   if (presorted && o->ntiles == 1) {
     o->from_host_rowptr = true;
     o->d_idx = d_col; o->d_y = d_y;
     return 0;
   }
   const size_t nruns = (size_t)o->ntiles * R;
-  o->h_run = pin.get<uint64_t>(nruns + 1);
-  if (!o->h_run) return fail(c, HPF_ENOMEM, "pinned run-pointer arena too small");
+  if (want_host_run) {
+    o->h_run = pin.get<uint64_t>(nruns + 1);
+    if (!o->h_run) return fail(c, HPF_ENOMEM, "pinned run-pointer arena too small");
+  }
   TRY(ensure(c, own_idx, own_idx_cap, nnz));
   if (d_y) TRY(ensure(c, own_y, own_y_cap, nnz));
   o->d_idx = *own_idx; o->d_y = d_y ? *own_y : nullptr;
+  uint64_t *d_run = dev.get<uint64_t>(nruns + 1);
+  if (!d_run) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  o->d_run = d_run;
   if (nnz == 0) {
-    memset(o->h_run, 0, (nruns + 1) * 8);
+    CU(cudaMemsetAsync(d_run, 0, (nruns + 1) * 8, c->stream));
+    if (want_host_run) memset(o->h_run, 0, (nruns + 1) * 8);
     return 0;
   }
   uint32_t *perm = dev.get<uint32_t>(nnz), *perm2 = dev.get<uint32_t>(nnz), *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz);
-  uint64_t *d_run = dev.get<uint64_t>(nruns + 1);
   void *d_tmp = dev.get<char>(cub_bytes);
-  if (!perm || !perm2 || !key || !key2 || !d_run || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  if (!perm || !perm2 || !key || !key2 || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
   size_t tmp_bytes = cub_bytes;
   const unsigned nb = (unsigned)((nnz + 255) / 256);
   iota_kernel<<<nb, 256, 0, c->stream>>>(perm, nnz);
@@ -642,7 +725,61 @@ int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, const uint32_t *d_row, con
   run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key, nnz, (uint32_t)nruns, d_run);
   c->launches += 2;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(o->h_run, d_run, (nruns + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (want_host_run) CU(cudaMemcpyAsync(o->h_run, d_run, (nruns + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+// ---- tile-sweep work list, built on the device ------------------------------------
+// phase 1: segments per run and their prefix sum; the total lands in pinned memory
+struct TileCount {
+  uint32_t *cnt = nullptr, *off = nullptr;
+  uint32_t *h_last = nullptr; // pinned {off[nruns-1], cnt[nruns-1]}
+  uint64_t nruns = 0;
+};
+int tile_count(hpf_ctx *c, Arena &dev, Arena &pin, const uint64_t *d_run, uint64_t nruns, TileCount *tc)
+{
+  tc->nruns = nruns;
+  tc->cnt = dev.get<uint32_t>(nruns);
+  tc->off = dev.get<uint32_t>(nruns);
+  tc->h_last = pin.get<uint32_t>(2);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nruns, c->stream);
+  void *d_tmp = dev.get<char>(scan_bytes);
+  if (!tc->cnt || !tc->off || !tc->h_last || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (tile count)");
+  tc->h_last[0] = tc->h_last[1] = 0;
+  if (nruns == 0) return 0;
+  seg_count_kernel<<<(unsigned)((nruns + 255) / 256), 256, 0, c->stream>>>(d_run, nruns, c->seg_len, tc->cnt);
+  CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, (const uint32_t *)tc->cnt, tc->off, (int64_t)nruns, c->stream));
+  c->launches += 1;
+  CU(cudaMemcpyAsync(&tc->h_last[0], tc->off + nruns - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(&tc->h_last[1], tc->cnt + nruns - 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+// phase 2 (after the total is known): emit, sort by (tile, descending length), tile pointers
+int tile_emit(hpf_ctx *c, Arena &scratch, const uint64_t *d_run, const TileCount &tc, uint32_t R, uint32_t ntiles, uint32_t nsegs, TilePlan *tp)
+{
+  tp->nsegs = nsegs; tp->ntiles = ntiles;
+  TRY(ensure(c, &tp->seg, &tp->seg_cap, nsegs));
+  TRY(ensure(c, &tp->tile_ptr, &tp->tile_ptr_cap, (size_t)ntiles + 1));
+  if (nsegs == 0) {
+    CU(cudaMemsetAsync(tp->tile_ptr, 0, ((size_t)ntiles + 1) * 4, c->stream));
+    return 0;
+  }
+  const uint32_t L = c->seg_len;
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint4 *)nullptr, (uint4 *)nullptr,
+                                  (int64_t)nsegs, 0, 32, c->stream);
+  TRY(arena_reserve(c, scratch, pad256((size_t)nsegs * 16) + 2 * pad256((size_t)nsegs * 4) + pad256(sort_bytes) + 4096));
+  uint4 *seg_u = scratch.get<uint4>(nsegs);
+  uint32_t *key_u = scratch.get<uint32_t>(nsegs), *key_s = scratch.get<uint32_t>(nsegs);
+  void *d_tmp = scratch.get<char>(sort_bytes);
+  if (!seg_u || !key_u || !key_s || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (tile emit)");
+  seg_emit_kernel<<<(unsigned)((tc.nruns + 255) / 256), 256, 0, c->stream>>>(d_run, tc.off, tc.nruns, R, L, seg_u, key_u);
+  CU(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, (const uint32_t *)key_u, key_s, (const uint4 *)seg_u, tp->seg, (int64_t)nsegs, 0,
+                                     bits_for((uint64_t)ntiles * (L + 1)), c->stream));
+  tile_ptr_kernel<<<(nsegs + 256) / 256, 256, 0, c->stream>>>(key_s, nsegs, L + 1, ntiles, tp->tile_ptr);
+  c->launches += 2;
+  CU(cudaGetLastError());
   return 0;
 }
 
@@ -664,13 +801,21 @@ int ensure_aux(hpf_ctx *c)
 int one_iteration(hpf_ctx *c)
 {
   MARK(0);
-  TRY(launch_sweep(c, c->th, c->be)); // user pass  (CSR): T_theta
+  TRY(launch_sweep(c, c->th, c->be)); // user pass (CSR; the tail items when the head runs as a tile sweep): T_theta
   MARK(1);
-  TRY(launch_sweep(c, c->be, c->th)); // item pass  (CSC): T_beta (local users only)
+  if (c->item_tile.on) { // item pass as a tile sweep over user blocks: T_beta accumulated with reductions
+    const size_t mk = (size_t)c->be.R * c->ld, mpad = c->bias ? (((size_t)c->be.R + 3) & ~(size_t)3) : 0;
+    CU(cudaMemsetAsync(c->redblock, 0, (mk + mpad) * sizeof(float), c->stream));
+    TRY(launch_tile_sweep(c, c->item_tile, c->be, c->th));
+  } else {
+    TRY(launch_sweep(c, c->be, c->th)); // item pass (CSC): T_beta (local users only)
+  }
   MARK(2);
   TRY(launch_combine(c, c->th));
   TRY(launch_combine(c, c->be));
   MARK(3);
+  TRY(launch_tile_sweep(c, c->head_tile, c->th, c->be)); // user pass, head items from shared memory: T_theta +=
+  MARK(7);
   const double n_glob = c->cfg.n_users_global ? (double)c->cfg.n_users_global : (double)c->cfg.n_users;
   if (c->jacobi) { // -novb: beta's rate uses the OLD (global) sum_u E[theta], hgaprec.cc:1278-1283
     if (c->nranks > 1 && !c->th_colsum_global) {
@@ -762,6 +907,23 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (const char *e = getenv("HPF_L2_TILE_MB")) { int v = atoi(e); if (v >= 0 && v <= 4096) n->l2_tile_bytes = (uint64_t)v << 20; }
   if (const char *e = getenv("HPF_L2_TILE_KB")) { int v = atoi(e); if (v >= 0) n->l2_tile_bytes = (uint64_t)v << 10; } // tests
   pick_sweep_shape(n);
+  {
+    // rows per shared-memory tile of the tile sweeps (packed K4 float4 per row, + bias terms)
+    int smem_optin = 0;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const size_t budget = smem_optin > 16384 ? (size_t)smem_optin - 2048 : 0;
+    const size_t per_row = (size_t)n->K4 * 16 + (n->bias ? 8 : 0);
+    uint32_t tr = (uint32_t)std::min<size_t>(budget / per_row, 4096);
+    tr &= ~31u;
+    n->tile_rows = tr >= 64 ? tr : 0; // too few rows per tile: tile sweeps off
+    n->tile_smem = (size_t)n->tile_rows * per_row;
+    if (const char *e = getenv("HPF_ITEM_TILE")) n->item_tile_mode = atoi(e);
+    if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
+    if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
+      const uint32_t v = (uint32_t)atoi(e);
+      if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }
+    }
+  }
   c = n;
   int rc = 0;
   do {
@@ -815,6 +977,7 @@ void hpf_destroy(hpf_ctx *c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto &p : c->allocs) cudaFree(p.first);
   if (c->dev_arena.base) cudaFree(c->dev_arena.base);
+  if (c->dev_arena2.base) cudaFree(c->dev_arena2.base);
   if (c->pin_arena.base) cudaFreeHost(c->pin_arena.base);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -837,67 +1000,188 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   Trace tr(c->stream);
   c->ratings_set = false;
   c->nnz = nnz;
+  c->item_tile.on = c->head_tile.on = false;
   c->pin_arena.pinned_host = true;
+  const uint32_t L = c->seg_len, TR = c->tile_rows;
   const uint32_t th_t = tiles_for(c, m, n), be_t = tiles_for(c, n, m);
-  size_t cub_bytes = 0;
+  // the item pass can run as a tile sweep over blocks of TR users when the run keys fit 32 bits
+  const uint64_t it_tiles = TR ? ((uint64_t)n + TR - 1) / TR : 0;
+  const bool try_item_tile = c->item_tile_mode != 0 && TR > 0 && nnz > 0 && it_tiles * m < 0xfffffff0ull;
+  const bool try_head_tile = c->head_tile_mode != 0 && TR > 0 && nnz > 0;
+  const bool want_deg = try_head_tile;
+  size_t cub_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
                                   (uint32_t *)nullptr, (int64_t)std::max<uint64_t>(nnz, 1), 0, 32, c->stream);
-  // the two orientations are built one after the other on the stream, so they share the device scratch
-  const size_t dev_need = pad256(((size_t)n + 1) * 8) + pad256(nnz * 4) +
-                          std::max(orientation_dev_bytes(nnz, n, th_t, cub_bytes), orientation_dev_bytes(nnz, m, be_t, cub_bytes));
-  const size_t pin_need = pad256(((size_t)th_t * n + 1) * 8) + pad256(((size_t)be_t * m + 1) * 8) +
-                          worklist_host_bytes(nnz, n, th_t, c->seg_len) + worklist_host_bytes(nnz, m, be_t, c->seg_len);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                (int64_t)std::max<uint64_t>(std::max<uint64_t>(nnz + 1, it_tiles * m), n), c->stream);
+  const size_t item_runs = try_item_tile ? (size_t)it_tiles * m : 0;
+  const size_t dev_need = pad256(((size_t)n + 1) * 8) + pad256(nnz * 4) + 8 * pad256((size_t)m * 4) +
+                          orientation_dev_bytes(nnz, m, (uint32_t)std::max<uint64_t>(be_t, it_tiles ? it_tiles : 1), cub_bytes) +
+                          orientation_dev_bytes(nnz, m, be_t, cub_bytes) + orientation_dev_bytes(nnz, n, th_t, cub_bytes) +
+                          2 * pad256(item_runs * 4) + 2 * pad256((size_t)n * 4 + 4) +
+                          2 * pad256((nnz + 1) * 4) + 2 * pad256(((size_t)n + 1) * 8) + 3 * pad256(scan_bytes) + (1u << 16);
+  const size_t pin_need = pad256(((size_t)th_t * n + 1) * 8) + pad256(((size_t)be_t * m + 1) * 8) + pad256(((size_t)n + 1) * 8) +
+                          pad256((size_t)m * 4) + worklist_host_bytes(nnz, n, th_t, L) + worklist_host_bytes(nnz, m, be_t, L) + (1u << 16);
   TRY(arena_reserve(c, c->dev_arena, dev_need));
   TRY(arena_reserve(c, c->pin_arena, pin_need));
   TRY(ensure(c, &c->csr_idx, &c->csr_idx_cap, nnz));
   if (y) TRY(ensure(c, &c->csr_y, &c->csr_y_cap, nnz));
   const uint8_t *d_y = y ? c->csr_y : nullptr;
+  Arena &dev = c->dev_arena, &pin = c->pin_arena;
   tr.mark("reserve");
 
-  // ---- device half, all asynchronous: upload, argument check, both orderings
-  uint64_t *d_rowptr = c->dev_arena.get<uint64_t>((size_t)n + 1);
-  uint32_t *d_rowof = c->dev_arena.get<uint32_t>(nnz);
-  if (!d_rowptr || !d_rowof) return fail(c, HPF_ENOMEM, "device set-up arena too small");
-  Orientation uo, io;
+  // ================= stage 1 (async): upload, check, item ordering, item degrees =================
+  uint64_t *d_rowptr = dev.get<uint64_t>((size_t)n + 1);
+  uint32_t *d_rowof = dev.get<uint32_t>(nnz);
+  uint32_t *h_bad = pin.get<uint32_t>(1);
+  if (!d_rowptr || !d_rowof || !h_bad) return fail(c, HPF_ENOMEM, "set-up arena too small");
+  *h_bad = 0;
   CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
+  const unsigned nb = (unsigned)((nnz + 255) / 256);
   if (nnz > 0) {
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    const unsigned nb = (unsigned)((nnz + 255) / 256);
     check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32); // every item index must be < n_items
     expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
     c->launches += 2;
   }
-  uint32_t *h_bad = c->pin_arena.get<uint32_t>(1);
-  if (!h_bad) return fail(c, HPF_ENOMEM, "pinned arena too small");
-  *h_bad = 0;
   CU(cudaMemcpyAsync(h_bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
-  const size_t dev_mark = c->dev_arena.off;
-  // item pass: rows = items, gathers user rows; users stay ascending inside a run
-  TRY(orient_device(c, c->dev_arena, c->pin_arena, c->csr_idx, d_rowof, d_y, false, m, n, &c->csc_idx, &c->csc_idx_cap, &c->csc_y,
-                    &c->csc_y_cap, cub_bytes, &io));
-  c->dev_arena.off = dev_mark; // stream order makes the scratch reusable
-  // user pass: rows = users (the CSR order itself), gathers item rows
-  TRY(orient_device(c, c->dev_arena, c->pin_arena, d_rowof, c->csr_idx, d_y, true, n, m, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
-                    &c->upass_y_cap, cub_bytes, &uo));
-  c->th_tiles = uo.ntiles; c->be_tiles = io.ntiles;
-
-  // ---- host half, overlapped with the device: the user-pass work list straight from the caller's row_ptr
-  HostWorkList uw, iw;
-  if (uo.from_host_rowptr) TRY(build_worklist_host(c, c->pin_arena, n, row_ptr, 1, &uw));
-  tr.mark("enqueue + user work list");
-  CU(cudaStreamSynchronize(c->stream));
-  tr.mark("device: upload, sorts");
-  if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
-  if (!uo.from_host_rowptr) TRY(build_worklist_host(c, c->pin_arena, n, uo.h_run, uo.ntiles, &uw));
-  TRY(build_worklist_host(c, c->pin_arena, m, io.h_run, io.ntiles, &iw));
-  tr.mark("item work list");
-  TRY(upload_worklist(c, c->th, uw, uo.d_idx, uo.d_y));
-  TRY(upload_worklist(c, c->be, iw, io.d_idx, io.d_y));
+  // item pass ordering: rows = items, gathers user rows (users ascending inside a run)
+  Orientation io, uo;
+  TileCount itc;
+  TRY(orient_device(c, dev, pin, nnz, c->csr_idx, d_rowof, d_y, false, m, n, try_item_tile ? TR : 0, !try_item_tile, &c->csc_idx,
+                    &c->csc_idx_cap, &c->csc_y, &c->csc_y_cap, cub_bytes, &io));
+  if (try_item_tile) TRY(tile_count(c, dev, pin, io.d_run, (uint64_t)io.ntiles * m, &itc));
+  // item degrees (from the item runs) and their descending order: the head items of the user pass
+  uint32_t *d_deg = nullptr, *d_degkey = nullptr, *d_degkey_s = nullptr, *d_id = nullptr, *d_id_s = nullptr, *h_degkey = nullptr;
+  if (want_deg) {
+    d_deg = dev.get<uint32_t>(m); d_degkey = dev.get<uint32_t>(m); d_degkey_s = dev.get<uint32_t>(m);
+    d_id = dev.get<uint32_t>(m); d_id_s = dev.get<uint32_t>(m);
+    h_degkey = pin.get<uint32_t>(m);
+    void *d_tmp = dev.get<char>(cub_bytes);
+    if (!d_deg || !d_degkey || !d_degkey_s || !d_id || !d_id_s || !h_degkey || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (degrees)");
+    degree_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(io.d_run, m, io.ntiles, d_deg);
+    neg_key_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(d_deg, m, d_degkey, d_id);
+    size_t tb = cub_bytes;
+    CU(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const uint32_t *)d_degkey, d_degkey_s, (const uint32_t *)d_id, d_id_s, (int64_t)m, 0, 32, c->stream));
+    c->launches += 2;
+    CU(cudaMemcpyAsync(h_degkey, d_degkey_s, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
-  tr.mark("work-list upload");
+  tr.mark("stage 1: upload, item order");
+  if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
+
+  // ================= decisions =================
+  uint32_t item_nsegs = 0;
+  bool item_tile = false;
+  if (try_item_tile) {
+    item_nsegs = itc.h_last[0] + itc.h_last[1];
+    // a segment costs one row-side load and one reduction; below ~3 nonzeros per segment the L2 gather is cheaper
+    item_tile = c->item_tile_mode == 1 || (item_nsegs > 0 && (double)nnz / item_nsegs >= 3.0);
+  }
+  uint32_t H = 0;
+  bool head_tile = false;
+  if (try_head_tile) {
+    H = std::min(TR, m);
+    uint64_t head_nnz = 0;
+    for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
+    head_tile = c->head_tile_mode == 1 || (double)head_nnz >= 0.2 * (double)nnz;
+  }
+
+  // ================= stage 2 (async): item work list; user-pass head / tail split =================
+  HostWorkList uw, iw;
+  if (item_tile) {
+    TRY(tile_emit(c, c->dev_arena2, io.d_run, itc, m, io.ntiles, item_nsegs, &c->item_tile));
+    to_slot_kernel<<<nb, 256, 0, c->stream>>>(c->csc_idx, nnz, TR);
+    c->launches++;
+    c->item_tile.on = true; c->item_tile.nnz = nnz; c->item_tile.tile0_count = 0;
+    c->item_tile.idx = c->csc_idx; c->item_tile.y = c->csc_y; c->item_tile.has_y = y != nullptr; // not owned: the item-ordered copy
+    c->item_tile.cpt = io.ntiles >= 4u * (uint32_t)c->sm_count ? 2u : std::max(2u, (8u * (uint32_t)c->sm_count + io.ntiles - 1) / io.ntiles);
+    // the gather kernel is not used for the item side: an empty work list
+    c->be.wl.nsegs = 0; c->be.wl.nmulti = 0; c->be.wl.npartial = 0;
+  } else if (try_item_tile) {
+    // fall back to the L2-tiled gather ordering (set-up cost only)
+    TRY(orient_device(c, dev, pin, nnz, c->csr_idx, d_rowof, d_y, false, m, n, 0, true, &c->csc_idx, &c->csc_idx_cap, &c->csc_y,
+                      &c->csc_y_cap, cub_bytes, &io));
+  }
+  uint64_t *h_tailptr = nullptr, *d_tailptr = nullptr, *d_headptr = nullptr;
+  TileCount htc;
+  uint64_t *h_counts = pin.get<uint64_t>(2); // {tail nnz, -}
+  if (!h_counts) return fail(c, HPF_ENOMEM, "pinned arena too small");
+  if (head_tile) {
+    TilePlan &hp = c->head_tile;
+    TRY(ensure(c, &hp.row_ids, &hp.row_ids_cap, H));
+    TRY(ensure(c, &hp.idx, &hp.idx_cap, nnz));
+    if (y) TRY(ensure(c, &hp.y, &hp.y_cap, nnz));
+    TRY(ensure(c, &c->tail_idx, &c->tail_idx_cap, nnz));
+    if (y) TRY(ensure(c, &c->tail_y, &c->tail_y_cap, nnz));
+    uint32_t *d_slot = dev.get<uint32_t>(m), *d_istail = dev.get<uint32_t>(nnz + 1), *d_tailpos = dev.get<uint32_t>(nnz + 1);
+    d_tailptr = dev.get<uint64_t>((size_t)n + 1); d_headptr = dev.get<uint64_t>((size_t)n + 1);
+    h_tailptr = pin.get<uint64_t>((size_t)n + 1);
+    void *d_tmp = dev.get<char>(scan_bytes);
+    if (!d_slot || !d_istail || !d_tailpos || !d_tailptr || !d_headptr || !h_tailptr || !d_tmp)
+      return fail(c, HPF_ENOMEM, "set-up arena too small (head split)");
+    CU(cudaMemcpyAsync(hp.row_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemsetAsync(d_slot, 0xff, (size_t)m * 4, c->stream));
+    head_slot_kernel<<<(H + 255) / 256, 256, 0, c->stream>>>(d_id_s, H, d_slot);
+    head_flag_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(c->csr_idx, d_slot, nnz, d_istail);
+    size_t sb = scan_bytes;
+    CU(cub::DeviceScan::ExclusiveSum(d_tmp, sb, (const uint32_t *)d_istail, d_tailpos, (int64_t)(nnz + 1), c->stream));
+    head_split_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, d_y, d_slot, d_tailpos, nnz, c->tail_idx, c->tail_y, hp.idx, hp.y);
+    split_ptr_kernel<<<(n + 256) / 256, 256, 0, c->stream>>>(d_rowptr, d_tailpos, n, d_tailptr, d_headptr);
+    c->launches += 4;
+    CU(cudaMemcpyAsync(h_tailptr, d_tailptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(tile_count(c, dev, pin, d_headptr, n, &htc)); // the head is ONE tile: runs = users
+  }
+  // the item-side host work list (gather mode) can be built while the device works on stage 2
+  if (!item_tile && !try_item_tile) { /* h_run arrived with stage 1 */
+    TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw));
+  }
+  if (!head_tile) { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
+    TRY(orient_device(c, dev, pin, nnz, d_rowof, c->csr_idx, d_y, true, n, m, 0, true, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
+                      &c->upass_y_cap, cub_bytes, &uo));
+    if (uo.from_host_rowptr) TRY(build_worklist_host(c, pin, n, row_ptr, 1, &uw));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  tr.mark("stage 2: work lists, split");
+
+  // ================= stage 3: remaining host work lists, head work list, uploads =================
+  if (!item_tile && try_item_tile) TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw));
+  if (head_tile) {
+    const uint64_t ntail = h_tailptr[n];
+    const uint32_t head_nsegs = htc.h_last[0] + htc.h_last[1];
+    TRY(tile_emit(c, c->dev_arena2, d_headptr, htc, n, 1, head_nsegs, &c->head_tile));
+    c->head_tile.on = true; c->head_tile.nnz = nnz - ntail; c->head_tile.tile0_count = H;
+    c->head_tile.has_y = y != nullptr;
+    c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
+    // tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
+    uint32_t *d_tailrow = nullptr;
+    if (tiles_for(c, m, n) > 1 && ntail > 0) {
+      d_tailrow = dev.get<uint32_t>(ntail);
+      if (!d_tailrow) return fail(c, HPF_ENOMEM, "set-up arena too small (tail rows)");
+      expand_rows_kernel<<<(unsigned)((ntail + 255) / 256), 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
+      c->launches++;
+    }
+    TRY(orient_device(c, dev, pin, ntail, d_tailrow, c->tail_idx, y ? c->tail_y : nullptr, true, n, m, 0, true, &c->upass_idx,
+                      &c->upass_idx_cap, &c->upass_y, &c->upass_y_cap, cub_bytes, &uo));
+    if (uo.from_host_rowptr) TRY(build_worklist_host(c, pin, n, h_tailptr, 1, &uw));
+    else {
+      CU(cudaStreamSynchronize(c->stream));
+      TRY(build_worklist_host(c, pin, n, uo.h_run, uo.ntiles, &uw));
+    }
+  } else if (!uo.from_host_rowptr) {
+    TRY(build_worklist_host(c, pin, n, uo.h_run, uo.ntiles, &uw));
+  }
+  tr.mark("stage 3: host work lists");
+  TRY(upload_worklist(c, c->th, uw, uo.d_idx, uo.d_y));
+  if (!item_tile) TRY(upload_worklist(c, c->be, iw, io.d_idx, io.d_y));
+  c->th_tiles = uo.ntiles; c->be_tiles = io.ntiles;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  tr.mark("uploads");
   c->ratings_set = true;
   return 0;
 }
@@ -1059,27 +1343,30 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
   CU(cudaSetDevice(c->cfg.device));
   TRY(check_ready(c));
   TRY(ensure_aux(c));
-  float acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+  // event order inside one_iteration: 0 user sweep 1 item pass 2 combine 3 user head tile 7 theta 4 all-reduce 5 beta 6
+  static const int seq[8] = { 0, 1, 2, 3, 7, 4, 5, 6 };
+  float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
   for (uint32_t it = 0; it < n_iters; ++it) {
     c->profiling = true;
     int rc = one_iteration(c);
     c->profiling = false;
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
       float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, c->pev[i], c->pev[i + 1]));
+      CU(cudaEventElapsedTime(&ms, c->pev[seq[i]], c->pev[seq[i + 1]]));
       acc[i] += ms;
     }
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->pev[0], c->pev[6]));
-    acc[6] += ms;
+    acc[7] += ms;
   }
   CU(cudaGetLastError());
   const float inv = 1.f / (float)n_iters;
-  out->sweep_user_ms = acc[0] * inv; out->sweep_item_ms = acc[1] * inv; out->combine_ms = acc[2] * inv;
-  out->update_theta_ms = acc[3] * inv; out->allreduce_ms = acc[4] * inv; out->update_beta_ms = acc[5] * inv;
-  out->total_ms = acc[6] * inv;
+  out->sweep_user_ms = (acc[0] + acc[3]) * inv; out->sweep_item_ms = acc[1] * inv; out->combine_ms = acc[2] * inv;
+  out->update_theta_ms = acc[4] * inv; out->allreduce_ms = acc[5] * inv; out->update_beta_ms = acc[6] * inv;
+  out->total_ms = acc[7] * inv;
+  out->sweep_user_head_ms = acc[3] * inv;
   return 0;
 }
 
@@ -1283,6 +1570,10 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
   out->last_iterate_ms = c->last_ms;
   out->sweep_group = c->sweep_g;
   out->sweep_vec = c->sweep_v;
+  out->tile_rows = c->tile_rows;
+  out->item_tiles = c->item_tile.on ? c->item_tile.ntiles : 0;
+  out->head_nnz = c->head_tile.on ? c->head_tile.nnz : 0;
+  out->tile_segments = (uint64_t)(c->item_tile.on ? c->item_tile.nsegs : 0) + (c->head_tile.on ? c->head_tile.nsegs : 0);
   return 0;
 }
 

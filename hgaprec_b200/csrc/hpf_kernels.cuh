@@ -24,6 +24,15 @@
 namespace hpf {
 
 constexpr int kSweepThreads = 256;
+// tuning knobs of the sweep kernels (tools/variants.sh builds alternatives side by side)
+#ifndef HPF_UNROLL_T
+#define HPF_UNROLL_T 1   // nonzeros of a chunk unrolled together
+#endif
+#ifndef HPF_SWEEP_MINBLOCKS
+#define HPF_SWEEP_MINBLOCKS 3
+#endif
+#define HPF_PRAGMA(x) _Pragma(#x)
+#define HPF_UNROLL(n) HPF_PRAGMA(unroll n)
 constexpr int kUpdateWarps = 8;
 constexpr float kZMin = 1e-30f;
 constexpr float kZMax = 1e30f;
@@ -44,18 +53,61 @@ __device__ __forceinline__ uint32_t ld_stream_u8(const uint8_t *p)
   return v;
 }
 
+// 1/x, one MUFU (max error ~1 ulp); callers keep x inside [kZMin, kZMax]
+__device__ __forceinline__ float frcp(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Blackwell packed fp32x2 arithmetic (FFMA2): two FMAs per issued instruction
+__device__ __forceinline__ float2 lo2(const float4 &v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 &v) { return make_float2(v.z, v.w); }
+template <int V> __device__ __forceinline__ float dot_rows(const float4 (&ar)[V], const float4 (&b)[V])
+{
+  float2 d = make_float2(0.f, 0.f), e = make_float2(0.f, 0.f); // two independent chains
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    d = __ffma2_rn(lo2(ar[v]), lo2(b[v]), d);
+    e = __ffma2_rn(hi2(ar[v]), hi2(b[v]), e);
+  }
+  d = __fadd2_rn(d, e);
+  return d.x + d.y;
+}
+template <int V> __device__ __forceinline__ void axpy_rows(float sc, const float4 (&b)[V], float4 (&acc)[V])
+{
+  const float2 s2 = make_float2(sc, sc);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float2 l = __ffma2_rn(s2, lo2(b[v]), lo2(acc[v]));
+    const float2 h = __ffma2_rn(s2, hi2(b[v]), hi2(acc[v]));
+    acc[v] = make_float4(l.x, l.y, h.x, h.y);
+  }
+}
+
 // digamma for x > 0 in fp32: upward recurrence to x >= 6, then the Stirling
 // series.  Replaces gsl_sf_psi at gpbase.hh:260,593,923.
 __device__ __forceinline__ float digammaf(float x)
 {
+  // psi(x) = psi(x + 6) - sum_{i<6} 1/(x + i); the sum is formed as ONE quotient p/q
+  // (q = prod (x+i), p = sum of the products leaving one factor out): one division instead of six
   float r = 0.f;
-  while (x < 6.f) {
-    r -= 1.f / x;
-    x += 1.f;
+  if (x < 6.f) {
+    float q = x, p = 1.f;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+      const float t = x + (float)i;
+      p = fmaf(p, t, q);
+      q *= t;
+    }
+    r = -__fdividef(p, q);
+    x += 6.f;
   }
-  const float f = 1.f / (x * x);
+  const float inv = __fdividef(1.f, x);
+  const float f = inv * inv;
   const float t = f * (-1.f / 12.f + f * (1.f / 120.f + f * (-1.f / 252.f + f * (1.f / 240.f))));
-  return r + logf(x) - 0.5f / x + t;
+  return r + __logf(x) - 0.5f * inv + t;
 }
 
 // ---------------------------------------------------------------------------
@@ -169,7 +221,7 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
 }
 
 template <int G, int V, bool BIAS>
-__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
+__global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kernel(const SweepArgs a)
 {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -204,58 +256,44 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
   const uint32_t *ip = a.idx + begin;
   const uint8_t *yp = a.y ? a.y + begin : nullptr;
   const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
+  // Lanes past the last float4 of a row re-read that float4 (their row-side value is 0 and their sums are
+  // never stored), so the loop carries no predicates.  Only the last of the V slots can be out of range.
+  const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
 
-  uint32_t cbuf = 0, ybuf = 1;
-  for (uint32_t j = 0; j < maxlen; ++j) {
-    if ((j & (G - 1)) == 0) {
-      const uint32_t jj = j + gl;
-      cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u;
-      ybuf = (yp != nullptr && jj < len) ? ld_stream_u8(yp + jj) : 1u;
-    }
-    const uint32_t c = __shfl_sync(0xffffffffu, cbuf, j & (G - 1), G);
-    const uint32_t yv = __shfl_sync(0xffffffffu, ybuf, j & (G - 1), G);
-    const bool active = j < len;
+  // chunks of G nonzeros: every lane of the group fetches one (index, rating), then the chunk is unrolled
+  // so that the gathers of one nonzero overlap the arithmetic of the previous one
+  for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
+    const uint32_t jj = j0 + gl;
+    const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row
+    const float ybuf = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f; // 0: no contribution
+    HPF_UNROLL(HPF_UNROLL_T)
+    for (int t = 0; t < G; ++t) {
+      const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
+      const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
+      float4 b[V];
+      const float4 *cp = acol + (size_t)c * a.ld4;
+#pragma unroll
+      for (int v = 0; v < V - 1; ++v) b[v] = ldg4(cp + gl + v * G);
+      b[V - 1] = ldg4(cp + q_last);
+      float2 caux = make_float2(0.f, 0.f);
+      if (BIAS) caux = __ldg(a.col_aux + c);
 
-    float4 b[V];
-    const float4 *cp = acol + (size_t)c * a.ld4;
+      float dot = dot_rows<V>(ar, b);
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const uint32_t q = gl + v * G;
-      b[v] = (active && q < a.K4) ? ldg4(cp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float2 caux = make_float2(0.f, 0.f);
-    if (BIAS && active) caux = __ldg(a.col_aux + c);
+      for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      float z = dot;
+      if (BIAS) z += raux.x * caux.y + caux.x * raux.y;
 
-    float dot = 0.f;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      dot = fmaf(ar[v].x, b[v].x, dot);
-      dot = fmaf(ar[v].y, b[v].y, dot);
-      dot = fmaf(ar[v].z, b[v].z, dot);
-      dot = fmaf(ar[v].w, b[v].w, dot);
-    }
-#pragma unroll
-    for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    float z = dot;
-    if (BIAS) z += raux.x * caux.y + caux.x * raux.y;
-
-    if (active) {
-      if (z > kZMin && z < kZMax) {
-        const float sc = (float)yv / z;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          acc[v].x = fmaf(sc, b[v].x, acc[v].x);
-          acc[v].y = fmaf(sc, b[v].y, acc[v].y);
-          acc[v].z = fmaf(sc, b[v].z, acc[v].z);
-          acc[v].w = fmaf(sc, b[v].w, acc[v].w);
-        }
-        if (BIAS) accb = fmaf(sc, caux.y, accb);
-      } else {
+      const bool ok = z > kZMin && z < kZMax;
+      const float sc = ok ? yv * frcp(z) : 0.f;
+      axpy_rows<V>(sc, b, acc);
+      if (BIAS) accb = fmaf(sc, caux.y, accb);
+      if (!ok && yv != 0.f) { // Z left the fp32 range: exact log-domain path (rare)
         SlowArgs sa;
         sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
         sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
         sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
-        sweep_slow_path<G, V, BIAS>(sa, row, c, (float)yv, lane);
+        sweep_slow_path<G, V, BIAS>(sa, row, c, yv, lane);
       }
     }
   }
@@ -273,6 +311,277 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
       else a.Tbpart[out - a.R] = accb;
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// K1b: tile sweep.  Same arithmetic as sweep_kernel, but the GATHERED factor rows
+// come from shared memory: a tile of up to tile_rows rows of the column side is
+// staged once per CTA (packed K floats per row) and every nonzero whose column
+// falls into that tile reads it from there -- the L2->SM gather, which bounds
+// sweep_kernel, disappears.  Two uses:
+//   item pass   rows = items, tiles = consecutive blocks of users; an item's
+//               nonzeros inside one user block form one segment;
+//   user pass   rows = users, ONE tile holding the most popular items (a Zipf
+//               head carries most of the nonzeros); the tail stays in sweep_kernel.
+// A row's sum is spread over many CTAs, so partial sums are added to T with
+// vector reductions (red.global.add.v4.f32) -- T is cleared (item pass) or
+// written by sweep_kernel (user pass) beforehand on the same stream.
+// Work: chunk c = (tile c / cpt, part c % cpt) covers an even share of the
+// tile's segments (tile_seg_ptr); CTAs take chunks round-robin.
+// ---------------------------------------------------------------------------
+#ifndef HPF_TILE_THREADS
+#define HPF_TILE_THREADS 640
+#endif
+constexpr int kTileThreads = HPF_TILE_THREADS;
+
+struct TileArgs {
+  const uint4 *seg;             // {begin_lo, begin_hi, row, len}, sorted by (tile, len desc)
+  const uint32_t *tile_seg_ptr; // [ntiles + 1]
+  uint32_t ntiles, cpt;         // chunks per tile
+  uint32_t tile_rows;           // rows per tile (last tile may hold fewer)
+  uint32_t C;                   // rows on the column side
+  const uint32_t *tile_row_ids; // explicit row list of tile 0 (single-tile use) or nullptr: tile t = rows [t*tile_rows, ...)
+  uint32_t tile0_count;         // rows in the explicit list
+  const uint32_t *idx;          // per nonzero: SLOT inside its tile
+  const uint8_t *y;
+  const float *Arow, *Acol;     // [. x ld]
+  float *T;                     // [R x ld]  +=
+  const float2 *row_aux, *col_aux;
+  float *Tb;                    // [R] +=
+  const float *ElogRow, *ElogCol, *ElogbRow, *ElogbCol;
+  float *Tdirect, *Tbdirect;
+  uint32_t *direct_flag;
+  unsigned long long *slow_count;
+  uint32_t K, K4, ld, ld4;
+};
+
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v)
+{
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int G, int V, bool BIAS>
+__global__ void __launch_bounds__(kTileThreads, 1) tile_sweep_kernel(const TileArgs a)
+{
+  extern __shared__ float4 tile_sm[]; // [tile_rows x K4] (+ float2 aux[tile_rows] with BIAS)
+  float2 *aux_sm = reinterpret_cast<float2 *>(tile_sm + (size_t)a.tile_rows * a.K4);
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const uint32_t gid = threadIdx.x / G;              // group inside the CTA
+  constexpr uint32_t kGroups = kTileThreads / G;
+  const uint32_t nchunks = a.ntiles * a.cpt;
+  uint32_t cur_tile = 0xffffffffu;
+  bool pq[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) pq[v] = (uint32_t)(gl + v * G) < a.K4;
+  // lanes past the last float4 of a row re-read it (row-side value 0, sums never stored): only the last slot can be
+  const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
+
+  for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const uint32_t tile = ch / a.cpt, part = ch % a.cpt;
+    // the tile's segments are sorted by length: part p takes every cpt-th one, so the parts carry equal work
+    const uint32_t t0 = __ldg(a.tile_seg_ptr + tile), t1 = __ldg(a.tile_seg_ptr + tile + 1);
+    if (t0 + part >= t1) continue;
+    const uint32_t nmine = (t1 - t0 - part + a.cpt - 1) / a.cpt; // segments t0 + part + cpt * i, i < nmine
+    const uint32_t tile_base = tile * a.tile_rows;
+    if (tile != cur_tile) { // stage the tile's factor rows (and bias terms)
+      __syncthreads();
+      const uint32_t nrows = a.tile_row_ids ? a.tile0_count : min(a.tile_rows, a.C - tile_base);
+      const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
+      for (uint32_t e = threadIdx.x; e < nrows * a.K4; e += kTileThreads) {
+        const uint32_t r = e / a.K4, q = e - r * a.K4;
+        const uint32_t src = a.tile_row_ids ? __ldg(a.tile_row_ids + r) : tile_base + r;
+        tile_sm[e] = __ldg(acol + (size_t)src * a.ld4 + q);
+      }
+      if (BIAS)
+        for (uint32_t r = threadIdx.x; r < nrows; r += kTileThreads)
+          aux_sm[r] = __ldg(a.col_aux + (a.tile_row_ids ? __ldg(a.tile_row_ids + r) : tile_base + r));
+      cur_tile = tile;
+      __syncthreads();
+    }
+    // the 32/G groups of a warp advance in lock-step over consecutive (equally long) segments
+    for (uint32_t ib = gid & ~(uint32_t)(32 / G - 1); ib < nmine; ib += kGroups) {
+      const uint32_t i = ib + (gid & (32 / G - 1));
+      const bool have = i < nmine;
+      const uint32_t sidx = t0 + part + a.cpt * i;
+      uint64_t begin = 0;
+      uint32_t row = 0, len = 0;
+      if (have) {
+        const uint4 s = __ldg(a.seg + sidx);
+        begin = (uint64_t)s.x | ((uint64_t)s.y << 32);
+        row = s.z;
+        len = s.w;
+      }
+      float4 ar[V], acc[V], b[V];
+      {
+        const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.ld4;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          ar[v] = (have && pq[v]) ? ldg4(rp + gl + v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          b[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float2 raux = make_float2(0.f, 0.f);
+      float accb = 0.f;
+      if (BIAS && have) raux = __ldg(a.row_aux + row);
+      const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
+      const uint32_t *ip = a.idx + begin;
+      const uint8_t *yp = a.y ? a.y + begin : nullptr;
+      for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
+        const uint32_t jj = j0 + gl;
+        const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // slot 0 past the end: valid
+        const float ybuf = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f;
+        HPF_UNROLL(HPF_UNROLL_T)
+        for (int t = 0; t < G; ++t) {
+          const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
+          const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
+          const float4 *cp = tile_sm + (size_t)c * a.K4;
+#pragma unroll
+          for (int v = 0; v < V - 1; ++v) b[v] = cp[gl + v * G];
+          b[V - 1] = cp[q_last];
+          float dot = dot_rows<V>(ar, b);
+#pragma unroll
+          for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+          float z = dot;
+          float2 caux = make_float2(0.f, 0.f);
+          if (BIAS) {
+            caux = aux_sm[c];
+            z += raux.x * caux.y + caux.x * raux.y;
+          }
+          const bool ok = z > kZMin && z < kZMax;
+          const float sc = ok ? yv * frcp(z) : 0.f;
+          axpy_rows<V>(sc, b, acc);
+          if (BIAS) accb = fmaf(sc, caux.y, accb);
+          if (!ok && yv != 0.f) { // Z left the fp32 range: exact log-domain path (rare)
+            SlowArgs sa;
+            sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
+            sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
+            sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
+            const uint32_t cg = a.tile_row_ids ? __ldg(a.tile_row_ids + c) : tile_base + c;
+            sweep_slow_path<G, V, BIAS>(sa, row, cg, yv, lane);
+          }
+        }
+      }
+      if (have && len > 0) {
+        float *dst = a.T + (size_t)row * a.ld;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (pq[v]) red_add_v4(dst + (size_t)(gl + v * G) * 4, acc[v]);
+        if (BIAS && gl == 0) atomicAdd(a.Tb + row, accb);
+      }
+    }
+  }
+}
+
+// ---- device-side work list of the tile sweep ----------------------------------
+// run q = tile * R + row covers nonzeros [run_ptr[q], run_ptr[q+1]); it is cut into
+// segments of <= L nonzeros.  cnt[q] = segments of run q.
+__global__ void seg_count_kernel(const uint64_t *run_ptr, uint64_t nruns, uint32_t L, uint32_t *cnt)
+{
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nruns) {
+    const uint64_t len = run_ptr[q + 1] - run_ptr[q];
+    cnt[q] = (uint32_t)((len + L - 1) / L);
+  }
+}
+
+// segments of run q go to slots [off[q], off[q] + cnt); key orders them by (tile, descending length)
+__global__ void seg_emit_kernel(const uint64_t *run_ptr, const uint32_t *off, uint64_t nruns, uint32_t R, uint32_t L,
+                                uint4 *seg, uint32_t *key)
+{
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nruns) return;
+  const uint64_t b0 = run_ptr[q], len = run_ptr[q + 1] - b0;
+  if (len == 0) return;
+  const uint32_t tile = (uint32_t)(q / R), row = (uint32_t)(q % R);
+  const uint32_t cnt = (uint32_t)((len + L - 1) / L);
+  uint32_t o = off[q];
+  for (uint32_t s = 0; s < cnt; ++s, ++o) {
+    const uint64_t sb = b0 + (uint64_t)s * L;
+    const uint32_t sl = (uint32_t)min((uint64_t)L, len - (uint64_t)s * L);
+    seg[o] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), row, sl);
+    key[o] = tile * (L + 1) + (L - sl);
+  }
+}
+
+// tile_ptr[t] = first sorted segment whose tile is >= t, t in [0, ntiles]
+__global__ void tile_ptr_kernel(const uint32_t *sorted_key, uint32_t nsegs, uint32_t Lp1, uint32_t ntiles, uint32_t *tile_ptr)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > nsegs) return;
+  const uint32_t prev = j == 0 ? 0u : sorted_key[j - 1] / Lp1 + 1u;
+  const uint32_t cur = j == nsegs ? ntiles + 1u : sorted_key[j] / Lp1 + 1u;
+  for (uint32_t t = prev; t < cur && t <= ntiles; ++t) tile_ptr[t] = j;
+}
+
+// column-side index -> slot inside its tile of tile_rows consecutive rows
+__global__ void to_slot_kernel(uint32_t *idx, uint64_t nnz, uint32_t tile_rows)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) idx[j] %= tile_rows;
+}
+
+// ---- head / tail split of the user pass ----------------------------------------
+// item degrees from the item-pass runs (run q = tile * R + item): no atomics on the hot items
+__global__ void degree_kernel(const uint64_t *run_ptr, uint32_t R, uint32_t ntiles, uint32_t *deg)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  uint64_t d = 0;
+  for (uint32_t t = 0; t < ntiles; ++t) {
+    const size_t q = (size_t)t * R + i;
+    d += run_ptr[q + 1] - run_ptr[q];
+  }
+  deg[i] = (uint32_t)d;
+}
+// keys that sort items by descending degree (ties by ascending id through the stable sort)
+__global__ void neg_key_kernel(const uint32_t *deg, uint32_t m, uint32_t *key, uint32_t *id)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { key[i] = 0xffffffffu - deg[i]; id[i] = i; }
+}
+// slot_of[item] = position among the H most popular items, or 0xffffffff
+__global__ void head_slot_kernel(const uint32_t *sorted_id, uint32_t H, uint32_t *slot_of)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < H) slot_of[sorted_id[r]] = r;
+}
+__global__ void head_flag_kernel(const uint32_t *col, const uint32_t *slot_of, uint64_t nnz, uint32_t *is_tail)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) is_tail[j] = slot_of[col[j]] == 0xffffffffu ? 1u : 0u;
+  else if (j == nnz) is_tail[j] = 0u; // sentinel: the exclusive scan's last entry is the tail total
+}
+// stable partition of the CSR nonzeros into a tail CSR (column ids) and a head list (slots),
+// both still ordered by user; tail_pos is the exclusive scan of is_tail
+__global__ void head_split_kernel(const uint32_t *col, const uint8_t *y, const uint32_t *slot_of, const uint32_t *tail_pos,
+                                  uint64_t nnz, uint32_t *tail_idx, uint8_t *tail_y, uint32_t *head_idx, uint8_t *head_y)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const uint32_t cc = col[j], sl = slot_of[cc];
+  const uint32_t tp = tail_pos[j];
+  if (sl == 0xffffffffu) {
+    tail_idx[tp] = cc;
+    if (y) tail_y[tp] = y[j];
+  } else {
+    const uint64_t hp = j - tp;
+    head_idx[hp] = sl;
+    if (y) head_y[hp] = y[j];
+  }
+}
+// row pointers of both parts from the scan: tail_ptr[u] = tail_pos[row_ptr[u]], head_ptr[u] = row_ptr[u] - tail_ptr[u]
+// (tail_pos has nnz + 1 entries: the last one is the tail total)
+__global__ void split_ptr_kernel(const uint64_t *row_ptr, const uint32_t *tail_pos, uint32_t n, uint64_t *tail_ptr,
+                                 uint64_t *head_ptr)
+{
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > n) return;
+  const uint64_t p = row_ptr[u];
+  const uint64_t tp = tail_pos[p];
+  tail_ptr[u] = tp;
+  head_ptr[u] = p - tp;
 }
 
 // ---------------------------------------------------------------------------
@@ -450,16 +759,25 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
   }
 }
 
-// colsum[k] = sum over blocks of partial[b][k], accumulated in double, fixed
-// order; also clears the side's direct_flag for the next iteration.
-__global__ void colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
-                                       float *colsum, uint32_t *direct_flag)
+// colsum[k] = sum over blocks of partial[b][k], accumulated in double in a fixed
+// order (one block per 32 columns, 8 row groups per block); also clears the side's
+// direct_flag for the next iteration.
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
+                                                             float *colsum, uint32_t *direct_flag)
 {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < Kp) {
-    double s = 0.0;
-    for (uint32_t b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * Kp + k];
-    colsum[k] = (float)s;
+  __shared__ double part[8][32];
+  const uint32_t kx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const uint32_t k = blockIdx.x * 32 + kx;
+  double s = 0.0;
+  if (k < Kp)
+    for (uint32_t b = g; b < nblocks; b += 8) s += (double)partial[(size_t)b * Kp + k];
+  part[g][kx] = s;
+  __syncthreads();
+  if (g == 0 && k < Kp) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][kx];
+    colsum[k] = (float)t;
   }
   if (direct_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *direct_flag = 0u;
 }

@@ -99,6 +99,10 @@ typedef struct hpf_stats {
                                 on the library's own stream)                       */
   uint32_t sweep_group;      /* lanes cooperating on one nonzero in the sweep      */
   uint32_t sweep_vec;        /* float4 values per lane                             */
+  uint32_t tile_rows;        /* factor rows per shared-memory tile (0: tile sweeps off) */
+  uint32_t item_tiles;       /* user blocks of the item-pass tile sweep (0: gather kernel) */
+  uint64_t head_nnz;         /* user-pass nonzeros served from the shared-memory head tile */
+  uint64_t tile_segments;    /* segments of both tile sweeps                        */
 } hpf_stats;
 
 /* Fill *cfg with the reference's defaults (all priors 0.3, device 0). */
@@ -178,13 +182,17 @@ HPF_API int hpf_get_stats(const hpf_ctx *ctx, hpf_stats *out);
  * library's stream around every kernel class and return the AVERAGE device
  * time per iteration of each (milliseconds).  Same arithmetic as hpf_iterate. */
 typedef struct hpf_iter_profile {
-  float sweep_user_ms;   /* phi sweep over the CSR (rows = users)              */
-  float sweep_item_ms;   /* phi sweep over the CSC (rows = items)              */
+  float sweep_user_ms;   /* phi sweep over the CSR (rows = users): gather kernel
+                            (tail items) + tile kernel (head items)            */
+  float sweep_item_ms;   /* phi sweep over the CSC (rows = items): tile kernel
+                            over user blocks, or the gather kernel             */
   float combine_ms;      /* partial-sum combine of split rows (both sides)     */
   float update_theta_ms; /* dense theta row update + column sums               */
   float allreduce_ms;    /* NCCL all-reduce of the item-side block (0 if 1 GPU) */
   float update_beta_ms;  /* dense beta row update + column sums                */
   float total_ms;        /* first kernel start to last kernel end              */
+  float sweep_user_head_ms; /* part of sweep_user_ms spent in the shared-memory
+                               tile sweep over the most popular items           */
 } hpf_iter_profile;
 HPF_API int hpf_iterate_profiled(hpf_ctx *ctx, uint32_t n_iters, hpf_iter_profile *out);
 

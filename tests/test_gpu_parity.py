@@ -191,13 +191,46 @@ def test_exact_fallback_when_products_underflow():
     assert not util.compare_states(got2, want, rel=6e-5, elog_abs=6e-5)
 
 
-def test_runs_are_bitwise_deterministic():
+def test_default_plan_is_bitwise_deterministic():
+    """The default plan (gather kernel on both sides, tile sweeps off) sums in a fixed order."""
     d, s = _oracle_case(2000, 700, 90000, 100, H.HIER | H.BIAS, seed=8)
-    a, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    a, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
     b, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    assert st["item_tiles"] == 0 and st["head_nnz"] == 0
     for gname in util.groups(a):
         for f in O.FIELDS:
             np.testing.assert_array_equal(a.p[gname][f], b.p[gname][f])
+
+
+def test_tile_sweep_runs_agree_to_summation_order(monkeypatch):
+    """The tile sweeps add partial sums with fp32 reductions whose order is not fixed."""
+    monkeypatch.setenv("HPF_ITEM_TILE", "1")
+    monkeypatch.setenv("HPF_HEAD_TILE", "1")
+    d, s = _oracle_case(2000, 700, 90000, 100, H.HIER | H.BIAS, seed=8)
+    a, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    b, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
+    assert st["item_tiles"] > 0 and st["head_nnz"] > 0
+    assert not util.compare_states(a, b, rel=1e-5, elog_abs=1e-5)
+
+
+@pytest.mark.parametrize("item_tile,head_tile,tile_rows", [("0", "0", None), ("1", "0", "64"), ("0", "1", "64"), ("1", "1", "96"),
+                                                           ("1", "1", None)])
+@pytest.mark.parametrize("flags", [H.HIER, H.BIAS])
+def test_every_sweep_plan_matches_oracle(monkeypatch, flags, item_tile, head_tile, tile_rows):
+    """gather-only, tile sweeps forced on one side or both, small forced tiles (many
+    user blocks, head smaller than the item set, rows split over segments)."""
+    monkeypatch.setenv("HPF_ITEM_TILE", item_tile)
+    monkeypatch.setenv("HPF_HEAD_TILE", head_tile)
+    monkeypatch.setenv("HPF_SEG_LEN", "64")
+    if tile_rows:
+        monkeypatch.setenv("HPF_TILE_ROWS", tile_rows)
+    d, s = _oracle_case(3000, 1500, 200000, 100, flags, seed=41)
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 2, nthreads=8)
+    got, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 2)
+    assert (st["item_tiles"] > 0) == (item_tile == "1") and (st["head_nnz"] > 0) == (head_tile == "1")
+    bad = util.compare_states(got, want, rel=4e-5, elog_abs=4e-5)
+    assert not bad, bad
+    assert st["slow_path_nnz"] == 0
 
 
 def test_errors_are_reported_not_fatal():
