@@ -84,6 +84,7 @@ def load_library():
     L.hpf_iterate.argtypes = [vp, u32]
     L.hpf_heldout_loglik.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_double)]
     L.hpf_topn.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
+    L.hpf_item_ranks.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.hpf_partition_users.argtypes = [vp, u32, u32, vp]
     L.hpf_comm_unique_id.argtypes = [vp, ctypes.c_size_t]
     L.hpf_comm_init.argtypes = [vp, cint, cint, vp, ctypes.c_size_t]
@@ -225,6 +226,17 @@ class Engine:
         scores = np.empty((len(users), topn), dtype=np.float32)
         self._check(self._L.hpf_topn(self._ctx, _p(users), len(users), _p(ep), _p(ei), int(topn), _p(items), _p(scores)))
         return items, scores
+
+    def item_ranks(self, users, excl_ptr, excl_idx, query_ptr, query_idx):
+        users = np.ascontiguousarray(users, dtype=np.uint32)
+        ep = np.ascontiguousarray(excl_ptr, dtype=np.uint64)
+        ei = np.ascontiguousarray(excl_idx, dtype=np.uint32)
+        qp = np.ascontiguousarray(query_ptr, dtype=np.uint64)
+        qi = np.ascontiguousarray(query_idx, dtype=np.uint32)
+        ranks = np.zeros(len(qi), dtype=np.uint32)
+        scores = np.zeros(len(qi), dtype=np.float32)
+        self._check(self._L.hpf_item_ranks(self._ctx, _p(users), len(users), _p(ep), _p(ei), _p(qp), _p(qi), _p(ranks), _p(scores)))
+        return ranks, scores
 
     def comm_init(self, rank, nranks, unique_id):
         buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)

@@ -1514,6 +1514,79 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
   return 0;
 }
 
+int hpf_item_ranks(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx,
+                   const uint64_t *query_ptr, const uint32_t *query_idx, uint32_t *rank_out, float *score_out)
+{
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  if (nu == 0) return 0;
+  if (!users || !query_ptr || !rank_out || !score_out) return fail(c, HPF_EINVAL, "null argument");
+  if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
+  if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
+  CU(cudaSetDevice(c->cfg.device));
+  const uint32_t n = c->th.R, m = c->be.R;
+  for (uint32_t a = 0; a < nu; ++a)
+    if (users[a] >= n) return fail(c, HPF_EINVAL, "users[%u]=%u >= n_users=%u", a, users[a], n);
+  const uint64_t nq = query_ptr[nu], nex = excl_ptr ? excl_ptr[nu] : 0;
+  if (query_ptr[0] != 0 || (excl_ptr && excl_ptr[0] != 0)) return fail(c, HPF_EINVAL, "pointer arrays must start at 0");
+  for (uint32_t a = 0; a < nu; ++a)
+    if (query_ptr[a + 1] < query_ptr[a] || (excl_ptr && excl_ptr[a + 1] < excl_ptr[a])) return fail(c, HPF_EINVAL, "pointer array not monotone at %u", a);
+  if (nq == 0) return 0;
+  if (!query_idx || (nex > 0 && !excl_idx)) return fail(c, HPF_EINVAL, "null index array");
+  for (uint64_t q = 0; q < nq; ++q)
+    if (query_idx[q] >= m) return fail(c, HPF_EINVAL, "query_idx[%llu]=%u >= n_items=%u", (unsigned long long)q, query_idx[q], m);
+  Scratch tmp;
+  uint32_t *d_users = nullptr, *d_exidx = nullptr, *d_rowof = nullptr, *d_qidx = nullptr, *d_rank = nullptr;
+  uint64_t *d_exptr = nullptr, *d_qptr = nullptr, *d_key = nullptr, *d_key2 = nullptr;
+  unsigned long long *d_qkey = nullptr;
+  float *d_score = nullptr;
+  CU(tmp.get(&d_users, nu)); CU(tmp.get(&d_exptr, (size_t)nu + 1)); CU(tmp.get(&d_qptr, (size_t)nu + 1));
+  CU(tmp.get(&d_qidx, nq)); CU(tmp.get(&d_rank, nq)); CU(tmp.get(&d_score, nq)); CU(tmp.get(&d_qkey, nq));
+  CU(cudaMemcpyAsync(d_users, users, (size_t)nu * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_qptr, query_ptr, ((size_t)nu + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_qidx, query_idx, nq * 4, cudaMemcpyHostToDevice, c->stream));
+  if (excl_ptr) CU(cudaMemcpyAsync(d_exptr, excl_ptr, ((size_t)nu + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  else CU(cudaMemsetAsync(d_exptr, 0, ((size_t)nu + 1) * 8, c->stream));
+  if (nex > 0) { // exclusion lists sorted by (user position, item), as in hpf_topn
+    CU(tmp.get(&d_exidx, nex)); CU(tmp.get(&d_rowof, nex)); CU(tmp.get(&d_key, nex)); CU(tmp.get(&d_key2, nex));
+    CU(cudaMemcpyAsync(d_exidx, excl_idx, nex * 4, cudaMemcpyHostToDevice, c->stream));
+    const unsigned nb = (unsigned)((nex + 255) / 256);
+    CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
+    check_range_kernel<<<nb, 256, 0, c->stream>>>(d_exidx, nex, m, c->scratch_u32);
+    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
+    topk::excl_key_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, d_exidx, nex, d_key);
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
+    size_t tmp_bytes = 0;
+    void *d_tmp = nullptr;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)nex, 0, 64, c->stream);
+    CU(tmp.get((char **)&d_tmp, tmp_bytes));
+    CU(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, (const uint64_t *)d_key, d_key2, (int64_t)nex, 0, 32 + bits_for(nu), c->stream));
+    topk::excl_unkey_kernel<<<nb, 256, 0, c->stream>>>(d_key2, nex, d_exidx);
+    c->launches += 4;
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad != 0) return fail(c, HPF_EINVAL, "excl_idx holds item %u >= n_items=%u", bad, m);
+  }
+  topk::RankArgs a;
+  a.nu = nu; a.m = m; a.K = c->K; a.ld = c->ld;
+  const size_t fixed = (size_t)topk::kRankWarps * c->K * 4;
+  uint32_t chunk = 64;
+  while (chunk > 32 && fixed + (size_t)chunk * ((c->K + 1) * 4 + topk::kRankWarps * 8) > (160u << 10)) chunk -= 32;
+  a.chunk = chunk;
+  a.users = d_users; a.Et = c->th.Ev; a.Eb = c->be.Ev;
+  a.Etb = c->bias ? c->th.b_Ev : nullptr; a.Ebb = c->bias ? c->be.b_Ev : nullptr;
+  a.excl_ptr = d_exptr; a.excl_sorted = d_exidx; a.q_ptr = d_qptr; a.q_idx = d_qidx; a.q_key = d_qkey;
+  a.rank_out = d_rank; a.score_out = d_score;
+  const size_t smem = fixed + (size_t)chunk * ((c->K + 1) * 4 + topk::kRankWarps * 8) + 16;
+  CU(cudaFuncSetAttribute(topk::rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk::rank_kernel<<<(nu + topk::kRankWarps - 1) / topk::kRankWarps, topk::kRankWarps * 32, smem, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rank_out, d_rank, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(score_out, d_score, nq * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int hpf_partition_users(const uint64_t *row_ptr, uint32_t n_users, uint32_t nranks, uint32_t *first)
 {
   if (!row_ptr || !first || nranks == 0) return fail(nullptr, HPF_EINVAL, "bad partition arguments");

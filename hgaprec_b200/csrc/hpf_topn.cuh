@@ -441,5 +441,92 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Item ranks (compute_itemrank, hgaprec.cc:1607-1701): for listed (user, query
+// item) pairs, the position of the item in the user's FULL descending list (same
+// scores, same exclusion rule and same tie order as the top-N: key = score bits,
+// ~item).  position = number of items whose key is larger.  Plain fp32 CUDA-core
+// kernel: one warp per user, 8 users per CTA share each staged chunk of item
+// rows; every score is produced by ONE routine in ONE order, so a query's own key
+// compares equal to itself exactly.  Sized for the report-window use of the
+// reference (thousands of test users); the C5-scale version belongs on the tensor
+// cores next to topn_kernel.
+// ---------------------------------------------------------------------------
+constexpr int kRankWarps = 8;
+
+struct RankArgs {
+  uint32_t nu, m, K, ld, chunk; // chunk: item rows staged per step (multiple of 32)
+  const uint32_t *users;
+  const float *Et, *Eb, *Etb, *Ebb; // E[theta], E[beta] (row stride ld), bias expectations or nullptr
+  const uint64_t *excl_ptr; const uint32_t *excl_sorted;
+  const uint64_t *q_ptr; const uint32_t *q_idx; // query items per listed user
+  unsigned long long *q_key; // scratch, one per query
+  uint32_t *rank_out; float *score_out;
+};
+
+__device__ __forceinline__ float rank_dot(const float *th, const float *be, uint32_t K)
+{
+  float s = 0.f;
+  for (uint32_t k = 0; k < K; ++k) s = fmaf(th[k], be[k], s);
+  return s;
+}
+
+__global__ void __launch_bounds__(kRankWarps * 32) rank_kernel(const RankArgs a)
+{
+  extern __shared__ float rsm[];
+  float *th_sm = rsm;                                   // [8][K]
+  float *be_sm = th_sm + (size_t)kRankWarps * a.K;      // [chunk][K + 1]
+  unsigned long long *key_sm = reinterpret_cast<unsigned long long *>(be_sm + (size_t)a.chunk * (a.K + 1)); // [8][chunk]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ua = blockIdx.x * kRankWarps + w; // position in the user list
+  const bool live = ua < a.nu;
+  const uint32_t u = live ? a.users[ua] : 0u;
+  for (uint32_t k = lane; k < a.K; k += 32) th_sm[(size_t)w * a.K + k] = live ? a.Et[(size_t)u * a.ld + k] : 0.f;
+  const float ub = (live && a.Etb) ? a.Etb[u] : 0.f;
+  const uint32_t *ex = a.excl_sorted + (live ? a.excl_ptr[ua] : 0);
+  const uint32_t exlen = live ? (uint32_t)(a.excl_ptr[ua + 1] - a.excl_ptr[ua]) : 0u;
+  const uint64_t q0 = live ? a.q_ptr[ua] : 0, q1 = live ? a.q_ptr[ua + 1] : 0;
+  __syncwarp();
+  const float *myth = th_sm + (size_t)w * a.K;
+  // the queries' own keys, with the same routine from global rows
+  for (uint64_t q = q0 + lane; q < q1; q += 32) {
+    const uint32_t it = a.q_idx[q];
+    float s = rank_dot(myth, a.Eb + (size_t)it * a.ld, a.K);
+    if (a.Etb) s += ub + a.Ebb[it];
+    uint32_t bits = __float_as_uint(s);
+    if ((int)bits < 0 || is_excluded(ex, exlen, it)) bits = 0u;
+    a.q_key[q] = ((unsigned long long)bits << 32) | (unsigned long long)(~it);
+    a.score_out[q] = __uint_as_float(bits);
+    a.rank_out[q] = 0u;
+  }
+  for (uint32_t i0 = 0; i0 < a.m; i0 += a.chunk) {
+    const uint32_t ni = min(a.chunk, a.m - i0);
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < ni * a.K; e += blockDim.x) {
+      const uint32_t r = e / a.K, k = e - r * a.K;
+      be_sm[(size_t)r * (a.K + 1) + k] = a.Eb[(size_t)(i0 + r) * a.ld + k];
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (uint32_t r = lane; r < ni; r += 32) {
+      const uint32_t it = i0 + r;
+      float s = rank_dot(myth, be_sm + (size_t)r * (a.K + 1), a.K);
+      if (a.Etb) s += ub + a.Ebb[it];
+      uint32_t bits = __float_as_uint(s);
+      if ((int)bits < 0 || is_excluded(ex, exlen, it)) bits = 0u;
+      key_sm[(size_t)w * a.chunk + r] = ((unsigned long long)bits << 32) | (unsigned long long)(~it);
+    }
+    __syncwarp();
+    const unsigned long long *mk = key_sm + (size_t)w * a.chunk;
+    for (uint64_t q = q0 + lane; q < q1; q += 32) {
+      const unsigned long long kq = a.q_key[q];
+      uint32_t cnt = 0;
+      for (uint32_t r = 0; r < ni; ++r) cnt += mk[r] > kq ? 1u : 0u;
+      a.rank_out[q] += cnt;
+    }
+    __syncwarp();
+  }
+}
+
 } // namespace topk
 } // namespace hpf

@@ -330,10 +330,68 @@ void HGAPRec::compute_precision(bool save_ranking_file)
   fflush(pf_);
 }
 
-// compute_itemrank needs the full rank of every test item; its device kernel is
-// the next step of the path.  Until then the files it
-// would write are not produced -- nothing is computed on the host instead.
-void HGAPRec::compute_itemrank(bool) {}
+// compute_itemrank (1607-1701): position of every test hit in the user's full descending list
+void HGAPRec::compute_itemrank(bool final)
+{
+  if (iter_ % 100 == 0 && iter_ > 0) final = true;
+  if (!final) return;
+  FILE *f = fopen(out("/itemrank.tsv").c_str(), "w");
+  FILE *itemf = fopen(out("/meanrank.txt").c_str(), "w");
+  if (!f || !itemf) {
+    printf("cannot open logl file:%s\n", strerror(errno));
+    exit(-1);
+  }
+  std::vector<uint32_t> users;
+  for (std::map<uint32_t, bool>::const_iterator it = sampled_users_.begin(); it != sampled_users_.end(); ++it) users.push_back(it->first);
+  std::vector<uint64_t> eptr, qptr(users.size() + 1, 0);
+  std::vector<uint32_t> eidx, qidx;
+  exclusions_of(users, &eptr, &eidx);
+  for (size_t a = 0; a < users.size(); ++a) { // the user's test items that count as hits (test_hit)
+    const uint32_t u = users[a];
+    for (HeldoutMap::const_iterator t = test_map_.lower_bound(Pair(u, 0)); t != test_map_.end() && t->first.first == u; ++t)
+      if (ratings_.test_hit(t->second)) qidx.push_back(t->first.second);
+    qptr[a + 1] = qidx.size();
+  }
+  std::vector<uint32_t> rank(qidx.size());
+  std::vector<float> pred(qidx.size());
+  if (!users.empty() &&
+      hpf_item_ranks(ctx_, users.data(), (uint32_t)users.size(), eptr.data(), eidx.data(), qptr.data(), qidx.data(), rank.data(), pred.data()) != 0)
+    die("hpf_item_ranks");
+  double sum_rank = 0, sum_reciprocal_rank = 0;
+  uint32_t total_users = 0;
+  for (size_t a = 0; a < users.size(); ++a) {
+    const uint32_t u = users[a];
+    // items the sorted list counts as ranked: those with no training rating (1662-1663)
+    std::vector<uint32_t> tr;
+    const std::vector<uint32_t> &it = ratings_.items_of(u);
+    for (size_t j = 0; j < it.size(); ++j)
+      if (ratings_.r(u, it[j]) > 0) tr.push_back(it[j]);
+    std::sort(tr.begin(), tr.end());
+    const uint32_t nranked = m_ - (uint32_t)(std::unique(tr.begin(), tr.end()) - tr.begin());
+    // the reference walks the list top-down: emit the hits by ascending position
+    std::vector<std::pair<uint32_t, uint64_t> > order;
+    for (uint64_t q = qptr[a]; q < qptr[a + 1]; ++q) order.push_back(std::make_pair(rank[q], q));
+    std::sort(order.begin(), order.end());
+    double rank_ui = 0, reciprocal_rank_ui = 0;
+    uint32_t ntestitems = 0;
+    for (size_t o = 0; o < order.size(); ++o) {
+      const uint64_t q = order[o].second;
+      const uint32_t j = order[o].first;
+      ntestitems++;
+      fprintf(f, "%d\t%d\t%.5f\t%d\t%d\n", u, qidx[q], pred[q], j, (int)ratings_.users_of(qidx[q]).size());
+      rank_ui += (j + 1);
+      reciprocal_rank_ui += 1 / (j + 1); // integer division, as in the reference (1683)
+    }
+    if (ntestitems > 0 && nranked > 0) {
+      sum_rank += (rank_ui / nranked) / ntestitems;
+      sum_reciprocal_rank += reciprocal_rank_ui / ntestitems;
+      total_users++;
+    }
+  }
+  fclose(f);
+  fprintf(itemf, "%d\t%.5f\t%.5f\n", total_users, (double)sum_rank / total_users, (double)sum_reciprocal_rank / total_users);
+  fclose(itemf);
+}
 
 bool HGAPRec::load_beta_and_theta()
 {

@@ -164,6 +164,17 @@ HPF_API int hpf_topn(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
  * the other ranks by any means (bench.py uses torch.distributed).  After this,
  * hpf_iterate all-reduces the item-side accumulators once per iteration and
  * hpf_heldout_loglik stays rank-local. */
+/* compute_itemrank's ranking (src/hgaprec.cc:1607-1701): for each listed local
+ * user and each of its query items (query_ptr: nu+1 entries into query_idx; the
+ * reference asks for the user's test items), the 0-based position of the item in
+ * the user's full descending score list -- same scores, same exclusion rule
+ * (excluded items score 0.0) and same tie order (ascending item) as hpf_topn --
+ * and its score.  rank_out / score_out: one entry per query. */
+HPF_API int hpf_item_ranks(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
+                   const uint64_t *excl_ptr, const uint32_t *excl_idx,
+                   const uint64_t *query_ptr, const uint32_t *query_idx,
+                   uint32_t *rank_out, float *score_out);
+
 /* Contiguous user ranges balanced by NONZEROS (not by user count) for nranks
  * shards: first_user_out[r] .. first_user_out[r+1] is rank r's range
  * (nranks + 1 entries, first 0, last n_users).  Pure host arithmetic on the CSR

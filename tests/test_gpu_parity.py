@@ -327,6 +327,43 @@ def test_topn_matches_oracle(name, n, m, nnz, k, flags, topn, iters):
         assert (scores[a][hit] == 0).all()
 
 
+@pytest.mark.parametrize("flags,k", [(H.HIER, 100), (H.BIAS, 20)])
+def test_item_ranks_match_full_sorted_list(flags, k):
+    """hpf_item_ranks against the oracle's complete sorted list (topn with topn = m)."""
+    n, m = 400, 900
+    d, s = _oracle_case(n, m, 30000, k, flags, seed=29)
+    s.iterate(d["row_ptr"], d["col_idx"], d["y"], 2, nthreads=8)
+    rng = np.random.default_rng(7)
+    users = rng.permutation(n)[:150].astype(np.uint32)
+    rp = d["row_ptr"].astype(np.int64)
+    excl = [d["col_idx"][rp[u]:rp[u + 1]] for u in users]
+    ep = np.zeros(len(users) + 1, np.uint64)
+    ep[1:] = np.cumsum([len(x) for x in excl])
+    ei = np.concatenate(excl).astype(np.uint32)
+    qs = [rng.choice(m, size=rng.integers(0, 25), replace=False).astype(np.uint32) for _ in users]
+    qs[2] = np.concatenate([qs[2], excl[2][:3]]).astype(np.uint32)  # queries that are excluded items: rank among the zeros
+    qp = np.zeros(len(users) + 1, np.uint64)
+    qp[1:] = np.cumsum([len(x) for x in qs])
+    qi = np.concatenate(qs).astype(np.uint32)
+    o_items, o_scores = s.topn(users, ep, ei, m)
+    with make_engine(s) as e:
+        util.push_state(e, s)
+        ranks, scores = e.item_ranks(users, ep, ei, qp, qi)
+    exact = 0
+    for a in range(len(users)):
+        pos = np.empty(m, np.int64)
+        pos[o_items[a]] = np.arange(m)
+        for q in range(int(qp[a]), int(qp[a + 1])):
+            it, want = qi[q], pos[qi[q]]
+            sc = o_scores[a][want]
+            assert abs(scores[q] - sc) <= 2e-5 * max(sc, 1e-12), (a, it)
+            # fp32 vs fp64 may swap near-ties: allow the position to move within the run of almost-equal scores
+            near = np.sum(np.abs(o_scores[a] - sc) <= 4e-6 * max(sc, 1e-30)) if sc > 0 else 1
+            assert abs(int(ranks[q]) - want) < near, (a, it, ranks[q], want)
+            exact += int(ranks[q]) == want
+    assert exact >= 0.98 * len(qi)
+
+
 def test_topn_rejects_bad_arguments():
     d, s = _oracle_case(50, 40, 500, 8, H.HIER, seed=3)
     with make_engine(s) as e:
