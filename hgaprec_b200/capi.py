@@ -46,7 +46,7 @@ class Stats(ctypes.Structure):
                 ("slow_path_nnz", ctypes.c_uint64), ("nnz", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
                 ("last_iterate_ms", ctypes.c_float), ("sweep_group", ctypes.c_uint32), ("sweep_vec", ctypes.c_uint32),
                 ("tile_rows", ctypes.c_uint32), ("item_tiles", ctypes.c_uint32), ("head_nnz", ctypes.c_uint64),
-                ("tile_segments", ctypes.c_uint64)]
+                ("tile_segments", ctypes.c_uint64), ("last_topn_ms", ctypes.c_float)]
 
 
 class IterProfile(ctypes.Structure):

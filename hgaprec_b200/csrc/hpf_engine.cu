@@ -190,7 +190,7 @@ struct hpf_ctx {
   int rank = 0, nranks = 1;
   // stats
   uint64_t launches = 0, iterations = 0;
-  float last_ms = 0.f;
+  float last_ms = 0.f, last_topn_ms = 0.f;
 };
 
 namespace {
@@ -1494,6 +1494,7 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
   if (!make_map(&map_b_hi, b_hi, m_pad, topk::kTileN) || !make_map(&map_b_lo, b_lo, m_pad, topk::kTileN))
     return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the item operand");
   CU(cudaFuncSetAttribute(topk::topn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk::kSmemBytes));
+  c->last_topn_ms = 0.f;
   for (uint32_t u0 = 0; u0 < nu; u0 += chunk_users) {
     const uint32_t cu = std::min(chunk_users, nu - u0);
     const uint32_t cu_pad = (cu + topk::kTileM - 1) / topk::kTileM * topk::kTileM;
@@ -1504,12 +1505,17 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
     topk::TopnArgs a;
     a.nu = cu; a.m = m; a.nkb = Kpad / topk::kBlockK; a.ntiles_n = m_pad / topk::kTileN; a.topn = topn;
     a.excl_ptr = d_exptr + u0; a.excl_sorted = d_exidx; a.cand = d_cand; a.items_out = d_items; a.scores_out = d_scores;
+    CU(cudaEventRecord(c->ev0, c->stream));
     topk::topn_kernel<<<cu_pad / topk::kTileM, topk::kThreads, topk::kSmemBytes, c->stream>>>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, a);
+    CU(cudaEventRecord(c->ev1, c->stream));
     c->launches += 2;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(items_out + (size_t)u0 * topn, d_items, (size_t)cu * topn * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(scores_out + (size_t)u0 * topn, d_scores, (size_t)cu * topn * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_topn_ms += ms;
   }
   return 0;
 }
@@ -1643,6 +1649,7 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
   out->last_iterate_ms = c->last_ms;
   out->sweep_group = c->sweep_g;
   out->sweep_vec = c->sweep_v;
+  out->last_topn_ms = c->last_topn_ms;
   out->tile_rows = c->tile_rows;
   out->item_tiles = c->item_tile.on ? c->item_tile.ntiles : 0;
   out->head_nnz = c->head_tile.on ? c->head_tile.nnz : 0;

@@ -204,38 +204,77 @@ __device__ __forceinline__ bool is_excluded(const uint32_t *lst, uint32_t len, u
 // Warp-cooperative: among the cnt (<= kCap) keys of one row keep the `keep`
 // largest (keep <= cnt), compacted to the front of buf in arbitrary order;
 // returns the smallest kept key (the row's new threshold).  Keys are distinct.
+// The keep-th largest key is found by a bitwise count-select in registers: first
+// on the score word (32-bit compares), then -- only among the keys that tie on
+// it -- on the item word.
 __device__ __forceinline__ unsigned long long warp_select(unsigned long long *buf, uint32_t cnt, uint32_t keep, int lane)
 {
   constexpr int PER = kCap / 32;
-  unsigned long long k[PER];
-  unsigned long long all_or = 0ull, all_and = ~0ull;
+  uint32_t hi[PER], lo[PER];
+  uint32_t hor = 0u, hand = 0xffffffffu;
 #pragma unroll
   for (int t = 0; t < PER; ++t) {
     const uint32_t j = lane + 32 * t;
-    k[t] = j < cnt ? buf[j] : 0ull; // 0 never beats a real key: real keys have ~item != 0 unless item == 2^32-1
-    if (j < cnt) { all_or |= k[t]; all_and &= k[t]; }
+    const unsigned long long k = j < cnt ? buf[j] : 0ull; // 0 is not a real key (that would be item 2^32-1)
+    hi[t] = (uint32_t)(k >> 32);
+    lo[t] = (uint32_t)k;
+    if (j < cnt) { hor |= hi[t]; hand &= hi[t]; }
   }
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    all_or |= __shfl_xor_sync(0xffffffffu, all_or, off);
-    all_and &= __shfl_xor_sync(0xffffffffu, all_and, off);
-  }
-  // bits on which the keys differ; the others are fixed in the answer
-  const unsigned long long vary = all_or & ~all_and;
-  unsigned long long thr = all_and; // greedy: largest T with count(key >= T) >= keep
-  for (int b = 63; b >= 0; --b) {
-    if (!((vary >> b) & 1ull)) continue;
-    const unsigned long long trial = thr | (1ull << b);
+  hor = __reduce_or_sync(0xffffffffu, hor);
+  hand = __reduce_and_sync(0xffffffffu, hand);
+  // largest T with count(hi >= T) >= keep, scanning only the bits on which the scores differ
+  uint32_t thr = hand;
+  for (uint32_t vary = hor & ~hand; vary != 0u;) {
+    const uint32_t b = 31u - (uint32_t)__clz(vary);
+    vary &= ~(1u << b);
+    const uint32_t trial = thr | (1u << b);
     uint32_t c = 0;
 #pragma unroll
-    for (int t = 0; t < PER; ++t) c += (k[t] >= trial) ? 1u : 0u;
+    for (int t = 0; t < PER; ++t) c += (hi[t] >= trial && lo[t] != 0u) ? 1u : 0u;
     c = __reduce_add_sync(0xffffffffu, c);
     if (c >= keep) thr = trial;
+  }
+  // keys with a larger score word are all kept; among those that tie on it, the `need` largest item words
+  uint32_t above = 0, ties = 0;
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const bool real = lo[t] != 0u;
+    above += (real && hi[t] > thr) ? 1u : 0u;
+    ties += (real && hi[t] == thr) ? 1u : 0u;
+  }
+  above = __reduce_add_sync(0xffffffffu, above);
+  ties = __reduce_add_sync(0xffffffffu, ties);
+  const uint32_t need = keep - above; // 1 <= need <= ties
+  uint32_t lthr = 0u;                  // smallest kept item word among the ties
+  if (need < ties) {
+    uint32_t lor = 0u, land = 0xffffffffu;
+#pragma unroll
+    for (int t = 0; t < PER; ++t)
+      if (lo[t] != 0u && hi[t] == thr) { lor |= lo[t]; land &= lo[t]; }
+    lor = __reduce_or_sync(0xffffffffu, lor);
+    land = __reduce_and_sync(0xffffffffu, land);
+    lthr = land;
+    for (uint32_t vary = lor & ~land; vary != 0u;) {
+      const uint32_t b = 31u - (uint32_t)__clz(vary);
+      vary &= ~(1u << b);
+      const uint32_t trial = lthr | (1u << b);
+      uint32_t c = 0;
+#pragma unroll
+      for (int t = 0; t < PER; ++t) c += (hi[t] == thr && lo[t] >= trial) ? 1u : 0u;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= need) lthr = trial;
+    }
+  } else {
+    uint32_t lmin = 0xffffffffu;
+#pragma unroll
+    for (int t = 0; t < PER; ++t)
+      if (lo[t] != 0u && hi[t] == thr) lmin = min(lmin, lo[t]);
+    lthr = __reduce_min_sync(0xffffffffu, lmin);
   }
   // compact: kept keys to the front (each lane writes its own, offsets by warp scan)
   uint32_t mine = 0;
 #pragma unroll
-  for (int t = 0; t < PER; ++t) mine += (k[t] >= thr && k[t] != 0ull) ? 1u : 0u;
+  for (int t = 0; t < PER; ++t) mine += (lo[t] != 0u && (hi[t] > thr || (hi[t] == thr && lo[t] >= lthr))) ? 1u : 0u;
   uint32_t incl = mine;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -246,9 +285,9 @@ __device__ __forceinline__ unsigned long long warp_select(unsigned long long *bu
   __syncwarp();
 #pragma unroll
   for (int t = 0; t < PER; ++t)
-    if (k[t] >= thr && k[t] != 0ull) buf[pos++] = k[t];
+    if (lo[t] != 0u && (hi[t] > thr || (hi[t] == thr && lo[t] >= lthr))) buf[pos++] = ((unsigned long long)hi[t] << 32) | lo[t];
   __syncwarp();
-  return thr;
+  return ((unsigned long long)thr << 32) | lthr;
 }
 
 // bitonic sort (descending) of P = 2^p <= kMaxTopN keys in shared memory by one warp
@@ -367,26 +406,46 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     unsigned long long tau = 0ull;                 // keys <= tau can no longer make the top-n
     uint32_t tau_hi = live ? 0u : 0xffffffffu;
     uint32_t cnt = 0;
+    uint32_t excur = 0;                            // cursor into the (ascending) exclusion list
     for (uint32_t j = 0; j < a.ntiles_n; ++j) {
       const uint32_t buf = j & 1u, tph = (j >> 1) & 1u;
-      mbar_wait(bar_tfull + 8 * buf, tph);
-      tc_fence_after();
       const uint32_t col0 = j * kTileN;
       const uint32_t ncols = a.m - col0 < (uint32_t)kTileN ? a.m - col0 : (uint32_t)kTileN;
+      // this tile's excluded columns as a 256-bit mask: the list is sorted, so a cursor walks it once per row
+      uint32_t mask[kTileN / 32];
+#pragma unroll
+      for (int w = 0; w < kTileN / 32; ++w) mask[w] = 0u;
+      while (excur < exlen) {
+        const uint32_t v = __ldg(ex + excur);
+        if (v >= col0 + (uint32_t)kTileN) break;
+        const uint32_t o = v - col0, bit = 1u << (o & 31u);
+#pragma unroll
+        for (int w = 0; w < kTileN / 32; ++w) mask[w] |= ((o >> 5) == (uint32_t)w) ? bit : 0u;
+        ++excur;
+      }
+      mbar_wait(bar_tfull + 8 * buf, tph);
+      tc_fence_after();
+#pragma unroll
       for (uint32_t c = 0; c < kTileN / 32; ++c) {
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + c * 32, r);
         tc_wait_ld();
         const uint32_t valid = ncols > c * 32 ? ncols - c * 32 : 0u;
+        const uint32_t mw = mask[c];                                   // excluded columns of this chunk
+        const uint32_t keepw = valid >= 32u ? 0xffffffffu : ((1u << valid) - 1u); // columns that exist
+        const uint32_t inv0 = ~(col0 + c * 32);                        // ~item of column 0; ~(x + i) == ~x - i
+        // branch-free filter: a score is appended when its float bits reach the row's threshold (scores
+        // are >= 0, so the bits order like the values).  An excluded item scores 0 (hgaprec.cc:1729-1735)
+        // and therefore only survives while the row has not seen topn candidates yet (tau_hi == 0).
+        // Appending on ">= the high word" is a superset of "key > tau"; the prune selects exactly.
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if ((uint32_t)i < valid && r[i] >= tau_hi) { // scores are >= 0: float bits order like the values
-            const uint32_t item = col0 + c * 32 + i;
-            uint32_t bits = r[i];
-            if ((int)bits < 0) bits = 0u;              // -0.0 / rounding noise below zero cannot occur; be safe
-            if (is_excluded(ex, exlen, item)) bits = 0u; // hgaprec.cc:1729-1735: keeps its slot with score 0
-            const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned long long)(~item);
-            if (key > tau) my[cnt++] = key;
+          uint32_t bits = ((mw >> i) & 1u) ? 0u : r[i];
+          if ((int)bits < 0) bits = 0u;
+          const bool push = ((keepw >> i) & 1u) && bits >= tau_hi;
+          if (push) {
+            my[cnt] = ((unsigned long long)bits << 32) | (unsigned long long)(inv0 - (uint32_t)i);
+            ++cnt;
           }
         }
       }

@@ -103,6 +103,8 @@ typedef struct hpf_stats {
   uint32_t item_tiles;       /* user blocks of the item-pass tile sweep (0: gather kernel) */
   uint64_t head_nnz;         /* user-pass nonzeros served from the shared-memory head tile */
   uint64_t tile_segments;    /* segments of both tile sweeps                        */
+  float    last_topn_ms;     /* device time of the scoring + selection kernel(s) of
+                                the last hpf_topn                                   */
 } hpf_stats;
 
 /* Fill *cfg with the reference's defaults (all priors 0.3, device 0). */
