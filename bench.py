@@ -293,6 +293,9 @@ def main():
         except Exception:
             pass
     roofline = {"bound": "hbm", "kernel": "hpf::sweep_kernel (2 launches / iteration: user pass + item pass)",
+                "note": "algorithmic bytes count a gathered factor row once per nonzero (SURVEY 8d); the rows are L2-resident at "
+                        "this size, so frac > 1 is expected and the binding limit is the L2->SM gather rate (see DESIGN.md 5)",
+                "l2_gather_TBps": (2 * nnz * (4 * ((k + 3) // 4 * 4) + 5)) / (sweep_ms * 1e-3) / 1e12,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes / 2,
@@ -347,6 +350,8 @@ def main():
                            "l2_policy": "inputs larger than L2 (ratings %.0f MB + factor rows %.0f MB per GPU vs 126 MB L2)"
                                         % ((2 * nnz * 5) / 1e6, (n + m) * k * 4 * 2 / 1e6),
                            "sweep_group": stats["sweep_group"], "sweep_vec": stats["sweep_vec"],
+                           "sweep_plan": "gather kernel on both passes" if not (stats["item_tiles"] or stats["head_nnz"]) else
+                                         "tile sweeps: item_tiles=%d head_nnz=%d" % (stats["item_tiles"], stats["head_nnz"]),
                            "state_init": "random Gamma(0.3+U,0.3+U) start (reference initialize() law), synthetic"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": clocks, "wall_s_timed_region": t_wall,
