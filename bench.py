@@ -50,15 +50,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+    def __init__(self, gpu_indices):
+        """One nvidia-smi process for all listed GPUs (rank 0 only: N pollers perturb the run)."""
+        self.gpu, self.proc, self.path = ",".join(str(g) for g in gpu_indices), None, None
 
     def start(self):
         if not shutil.which("nvidia-smi"):
             return
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
-        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits", "-lms", "100"],
                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
@@ -254,18 +255,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps.  The clock sampler
+    # (one nvidia-smi for all GPUs, on rank 0) starts BEFORE the warm-up: its start-up enumerates the
+    # devices and would otherwise land inside the ~100 ms timed region.
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+        time.sleep(1.0)
+    barrier()
     eng.iterate(args.warmup)
     l0 = eng.stats()["kernel_launches"]
-    sampler = ClockSampler(dev)
     barrier()
-    sampler.start()
     t_wall = time.time()
     eng.iterate(args.steps)  # CUDA events on the library's stream bracket exactly these K steps
     ms = eng.stats()["last_iterate_ms"]
     barrier()
     t_wall = time.time() - t_wall
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     launches = eng.stats()["kernel_launches"] - l0
     if dist is not None:
         t = torch.tensor([ms], device="cuda")

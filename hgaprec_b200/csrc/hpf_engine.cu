@@ -175,6 +175,7 @@ struct hpf_ctx {
   int item_tile_mode = 0, head_tile_mode = 0; // 0 off (default: measured slower than the gather kernel), 1 forced, -1 auto
   uint32_t th_tiles = 1, be_tiles = 1;
   uint64_t l2_tile_bytes = 32ull << 20; // factor rows of one gather tile (0: no tiling)
+  bool l2_tile_forced = false;          // HPF_L2_TILE_KB (tests): ignore the run-length cap
   uint32_t *scratch_u32 = nullptr;
   uint32_t seg_len = 512;
   int sweep_g = 0, sweep_v = 0;
@@ -502,13 +503,18 @@ int bits_for(uint64_t nvalues)
   return b;
 }
 
-// how many tiles the gathered side (C rows of ld floats) is cut into
-uint32_t tiles_for(const hpf_ctx *c, uint32_t C, uint32_t R)
+// How many tiles the gathered side (C rows of ld floats) is cut into.  Tiling keeps the gathers of one
+// pass inside an L2-sized window, but every (row, tile) run becomes a segment with its own partial
+// row: it only pays while runs stay long (measured: Netflix-scale item pass 6.2 -> 3.8 ms with 8 tiles
+// of ~5.7K-nonzero rows; MSD scale, ~4 nonzeros per run, 13.7 -> 30.7 ms).  So the tile count is also
+// capped by an average of >= 64 nonzeros per run.
+uint32_t tiles_for(const hpf_ctx *c, uint32_t C, uint32_t R, uint64_t nnz)
 {
   if (c->l2_tile_bytes == 0) return 1;
   const uint64_t bytes = (uint64_t)C * c->ld * sizeof(float);
   if (bytes <= 2 * c->l2_tile_bytes) return 1;
   uint64_t t = (bytes + c->l2_tile_bytes - 1) / c->l2_tile_bytes;
+  if (!c->l2_tile_forced) t = std::min<uint64_t>(t, std::max<uint64_t>(1, nnz / ((uint64_t)std::max(R, 1u) * 64)));
   while (t > 1 && t * (uint64_t)R >= 0xfffffff0ull) --t; // the composite key is 32 bits
   return (uint32_t)std::min<uint64_t>(t, C);
 }
@@ -679,7 +685,7 @@ int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, uint64_t nnz, const uint32
     o->tile_cols = force_tile_cols;
     o->ntiles = (uint32_t)(((uint64_t)C + force_tile_cols - 1) / force_tile_cols);
   } else {
-    o->ntiles = tiles_for(c, C, R);
+    o->ntiles = tiles_for(c, C, R, nnz);
     o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
   }
   if (presorted && o->ntiles == 1) {
@@ -905,7 +911,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   if (const char *e = getenv("HPF_SEG_LEN")) { int v = atoi(e); if (v >= 8 && v <= 65536) n->seg_len = v; }
   if (const char *e = getenv("HPF_L2_TILE_MB")) { int v = atoi(e); if (v >= 0 && v <= 4096) n->l2_tile_bytes = (uint64_t)v << 20; }
-  if (const char *e = getenv("HPF_L2_TILE_KB")) { int v = atoi(e); if (v >= 0) n->l2_tile_bytes = (uint64_t)v << 10; } // tests
+  if (const char *e = getenv("HPF_L2_TILE_KB")) { int v = atoi(e); if (v >= 0) { n->l2_tile_bytes = (uint64_t)v << 10; n->l2_tile_forced = true; } } // tests
   pick_sweep_shape(n);
   {
     // rows per shared-memory tile of the tile sweeps (packed K4 float4 per row, + bias terms)
@@ -1003,7 +1009,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   c->item_tile.on = c->head_tile.on = false;
   c->pin_arena.pinned_host = true;
   const uint32_t L = c->seg_len, TR = c->tile_rows;
-  const uint32_t th_t = tiles_for(c, m, n), be_t = tiles_for(c, n, m);
+  const uint32_t th_t = tiles_for(c, m, n, nnz), be_t = tiles_for(c, n, m, nnz);
   // the item pass can run as a tile sweep over blocks of TR users when the run keys fit 32 bits
   const uint64_t it_tiles = TR ? ((uint64_t)n + TR - 1) / TR : 0;
   const bool try_item_tile = c->item_tile_mode != 0 && TR > 0 && nnz > 0 && it_tiles * m < 0xfffffff0ull;
@@ -1159,7 +1165,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
     // tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
     uint32_t *d_tailrow = nullptr;
-    if (tiles_for(c, m, n) > 1 && ntail > 0) {
+    if (tiles_for(c, m, n, ntail) > 1 && ntail > 0) {
       d_tailrow = dev.get<uint32_t>(ntail);
       if (!d_tailrow) return fail(c, HPF_ENOMEM, "set-up arena too small (tail rows)");
       expand_rows_kernel<<<(unsigned)((ntail + 255) / 256), 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
