@@ -20,6 +20,7 @@
 #include "../../include/hpf_cuda.h"
 #include "hpf_kernels.cuh"
 #include "hpf_topn.cuh"
+#include "hpf_head.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -119,6 +120,18 @@ struct TilePlan {       // work of one tile_sweep_kernel launch
   bool has_y = false;
 };
 
+struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
+  bool on = false;
+  uint32_t *Yw = nullptr; size_t Yw_cap = 0;          // dense head ratings, as 32-bit words
+  uint32_t *head_ids = nullptr; size_t head_ids_cap = 0;
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  size_t a_hi_cap = 0, a_lo_cap = 0, b_hi_cap = 0, b_lo_cap = 0;
+  float *dB_part = nullptr; size_t dB_part_cap = 0;   // per-CTA partial sums of the head items' T_beta rows
+  uint32_t ntiles = 0, nhead = 0;
+  uint64_t head_nnz = 0;
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+};
+
 struct WorkList {       // segments of one orientation, sorted by descending length
   uint4 *seg = nullptr;
   uint32_t *seg_out = nullptr;
@@ -170,6 +183,8 @@ struct hpf_ctx {
   size_t csr_idx_cap = 0, csr_y_cap = 0, csc_idx_cap = 0, csc_y_cap = 0, upass_idx_cap = 0, upass_y_cap = 0;
   Arena dev_arena, dev_arena2, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
+  DensePlan dense;               // the most popular items as a dense block on the tensor cores
+  int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 25 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
   uint32_t tile_rows = 0; size_t tile_smem = 0;
   int item_tile_mode = 0, head_tile_mode = 0; // 0 off (default: measured slower than the gather kernel), 1 forced, -1 auto
@@ -557,20 +572,25 @@ size_t worklist_host_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L
   return pad256(segs * sizeof(uint4)) + pad256(segs * 4) + 3 * pad256((size_t)R * 4) + 4096;
 }
 
-int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr, uint32_t ntiles, HostWorkList *out)
+// skip (optional, R flags): rows that get NO segment at all, not even the empty one that clears T --
+// the head items of the dense-head plan, whose T rows belong to head_kernel.
+int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr, uint32_t ntiles, HostWorkList *out,
+                        const std::vector<uint8_t> *skip = nullptr)
 {
   const uint32_t L = c->seg_len;
+  auto skipped = [&](uint32_t r) { return skip != nullptr && (*skip)[r] != 0; };
   std::vector<uint32_t> segcnt(R, 0);
   for (uint32_t t = 0; t < ntiles; ++t) {
     const uint64_t *pt = ptr + (size_t)t * R;
     for (uint32_t r = 0; r < R; ++r) {
       const uint64_t len = pt[r + 1] - pt[r];
-      if (len) segcnt[r] += (uint32_t)((len + L - 1) / L);
+      if (len && !skipped(r)) segcnt[r] += (uint32_t)((len + L - 1) / L);
     }
   }
   uint64_t nsegs64 = 0;
   uint32_t nmulti = 0;
   for (uint32_t r = 0; r < R; ++r) {
+    if (skipped(r)) continue;
     nsegs64 += segcnt[r] ? segcnt[r] : 1;
     nmulti += segcnt[r] > 1;
   }
@@ -600,6 +620,7 @@ int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr,
     // counting sort by length, descending: bucket b holds length L - b
     std::fill(bucket.begin(), bucket.end(), 0u);
     for (uint32_t r = 0; r < R; ++r) {
+      if (skipped(r)) continue;
       const uint64_t len = pt[r + 1] - pt[r];
       if (len == 0) {
         if (t == 0 && segcnt[r] == 0) bucket[L + 1]++; // a row without nonzeros still clears its T row
@@ -611,6 +632,7 @@ int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr,
     for (uint32_t b = 1; b < L + 2; ++b) bucket[b] += bucket[b - 1];
     const uint32_t tile_segs = bucket[L + 1];
     for (uint32_t r = 0; r < R; ++r) {
+      if (skipped(r)) continue;
       const uint64_t b0 = pt[r], len = pt[r + 1] - pt[r];
       if (len == 0) {
         if (t == 0 && segcnt[r] == 0) {
@@ -789,6 +811,54 @@ int tile_emit(hpf_ctx *c, Arena &scratch, const uint64_t *d_run, const TileCount
   return 0;
 }
 
+PFN_cuTensorMapEncodeTiled_v12000 tensormap_encoder()
+{
+  static PFN_cuTensorMapEncodeTiled_v12000 fnp = nullptr;
+  if (!fnp) {
+    cudaDriverEntryPointQueryResult qres;
+    void *fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn)
+      fnp = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  return fnp;
+}
+
+// K-major bf16 matrix [rows x cols] -> tensor map with 128B-swizzled boxes of [64 cols x box_rows]
+bool make_bf16_map(CUtensorMap *map, void *ptr, uint64_t rows, uint32_t cols, uint32_t box_rows)
+{
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensormap_encoder();
+  if (!encode) return false;
+  cuuint64_t dims[2] = { cols, rows };
+  cuuint64_t strides[1] = { (cuuint64_t)cols * 2 };
+  cuuint32_t box[2] = { 64, box_rows };
+  cuuint32_t estr[2] = { 1, 1 };
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// dense head of one iteration: operand splits, head rows of T_beta cleared, then the tcgen05 kernel
+int launch_dense_head(hpf_ctx *c)
+{
+  DensePlan &d = c->dense;
+  if (!d.on) return 0;
+  const uint32_t n = c->th.R, n_pad = d.ntiles * head::kUsers;
+  topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->K, nullptr, 0, nullptr, n, n_pad, head::kFact, d.a_hi, d.a_lo);
+  topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, d.head_ids, d.nhead, head::kHead, head::kFact, d.b_hi, d.b_lo);
+  head::HeadArgs a;
+  a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
+  a.Y = reinterpret_cast<const uint8_t *>(d.Yw); a.head_ids = d.head_ids;
+  a.T_theta = c->th.T; a.dB_part = d.dB_part;
+  a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
+  a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
+  CU(cudaFuncSetAttribute(head::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
+  const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
+  head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi, d.map_b_lo, a);
+  head::head_reduce_kernel<<<d.nhead, 128, 0, c->stream>>>(d.dB_part, grid, d.head_ids, c->Kp, c->ld, c->be.T);
+  c->launches += 4;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int ensure_aux(hpf_ctx *c)
 {
   if (!c->bias || !c->aux_dirty) return 0;
@@ -821,6 +891,7 @@ int one_iteration(hpf_ctx *c)
   TRY(launch_combine(c, c->be));
   MARK(3);
   TRY(launch_tile_sweep(c, c->head_tile, c->th, c->be)); // user pass, head items from shared memory: T_theta +=
+  TRY(launch_dense_head(c)); // or the dense head block on tcgen05: T_theta +=, T_beta[head items] +=
   MARK(7);
   const double n_glob = c->cfg.n_users_global ? (double)c->cfg.n_users_global : (double)c->cfg.n_users;
   if (c->jacobi) { // -novb: beta's rate uses the OLD (global) sum_u E[theta], hgaprec.cc:1278-1283
@@ -925,6 +996,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     n->tile_smem = (size_t)n->tile_rows * per_row;
     if (const char *e = getenv("HPF_ITEM_TILE")) n->item_tile_mode = atoi(e);
     if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
+    if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
     if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
       const uint32_t v = (uint32_t)atoi(e);
       if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }
@@ -1014,7 +1086,9 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   const uint64_t it_tiles = TR ? ((uint64_t)n + TR - 1) / TR : 0;
   const bool try_item_tile = c->item_tile_mode != 0 && TR > 0 && nnz > 0 && it_tiles * m < 0xfffffff0ull;
   const bool try_head_tile = c->head_tile_mode != 0 && TR > 0 && nnz > 0;
-  const bool want_deg = try_head_tile;
+  const bool try_dense = c->dense_head_mode != 0 && !c->bias && c->Kp <= (uint32_t)head::kFact && nnz > 0 && !try_item_tile;
+  const bool want_deg = try_head_tile || try_dense;
+  c->dense.on = false;
   size_t cub_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
                                   (uint32_t *)nullptr, (int64_t)std::max<uint64_t>(nnz, 1), 0, 32, c->stream);
@@ -1061,6 +1135,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   if (try_item_tile) TRY(tile_count(c, dev, pin, io.d_run, (uint64_t)io.ntiles * m, &itc));
   // item degrees (from the item runs) and their descending order: the head items of the user pass
   uint32_t *d_deg = nullptr, *d_degkey = nullptr, *d_degkey_s = nullptr, *d_id = nullptr, *d_id_s = nullptr, *h_degkey = nullptr;
+  uint32_t *h_headid = nullptr;
   if (want_deg) {
     d_deg = dev.get<uint32_t>(m); d_degkey = dev.get<uint32_t>(m); d_degkey_s = dev.get<uint32_t>(m);
     d_id = dev.get<uint32_t>(m); d_id_s = dev.get<uint32_t>(m);
@@ -1073,6 +1148,9 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     CU(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const uint32_t *)d_degkey, d_degkey_s, (const uint32_t *)d_id, d_id_s, (int64_t)m, 0, 32, c->stream));
     c->launches += 2;
     CU(cudaMemcpyAsync(h_degkey, d_degkey_s, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    h_headid = pin.get<uint32_t>(head::kHead);
+    if (!h_headid) return fail(c, HPF_ENOMEM, "pinned arena too small");
+    CU(cudaMemcpyAsync(h_headid, d_id_s, (size_t)std::min<uint32_t>(m, head::kHead) * 4, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -1095,6 +1173,22 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
     head_tile = c->head_tile_mode == 1 || (double)head_nnz >= 0.2 * (double)nnz;
   }
+  // dense head on the tensor cores: the kHead most popular items, when they carry enough of the nonzeros
+  bool dense_head = false;
+  std::vector<uint8_t> skip_item;
+  if (try_dense && !head_tile) {
+    H = std::min<uint32_t>(head::kHead, m);
+    uint64_t head_nnz = 0;
+    for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
+    dense_head = c->dense_head_mode == 1 || (double)head_nnz >= 0.25 * (double)nnz;
+    if (dense_head) {
+      c->dense.head_nnz = head_nnz;
+      skip_item.assign(m, 0);
+      for (uint32_t r = 0; r < H; ++r) skip_item[h_headid[r]] = 1; // the item pass has no rows for head items
+    }
+  }
+  const bool split_head = head_tile || dense_head;
+  const std::vector<uint8_t> *skip_ptr = dense_head ? &skip_item : nullptr;
 
   // ================= stage 2 (async): item work list; user-pass head / tail split =================
   HostWorkList uw, iw;
@@ -1116,11 +1210,13 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   TileCount htc;
   uint64_t *h_counts = pin.get<uint64_t>(2); // {tail nnz, -}
   if (!h_counts) return fail(c, HPF_ENOMEM, "pinned arena too small");
-  if (head_tile) {
+  if (split_head) {
     TilePlan &hp = c->head_tile;
-    TRY(ensure(c, &hp.row_ids, &hp.row_ids_cap, H));
-    TRY(ensure(c, &hp.idx, &hp.idx_cap, nnz));
-    if (y) TRY(ensure(c, &hp.y, &hp.y_cap, nnz));
+    if (head_tile) {
+      TRY(ensure(c, &hp.row_ids, &hp.row_ids_cap, H));
+      TRY(ensure(c, &hp.idx, &hp.idx_cap, nnz));
+      if (y) TRY(ensure(c, &hp.y, &hp.y_cap, nnz));
+    }
     TRY(ensure(c, &c->tail_idx, &c->tail_idx_cap, nnz));
     if (y) TRY(ensure(c, &c->tail_y, &c->tail_y_cap, nnz));
     uint32_t *d_slot = dev.get<uint32_t>(m), *d_istail = dev.get<uint32_t>(nnz + 1), *d_tailpos = dev.get<uint32_t>(nnz + 1);
@@ -1129,23 +1225,47 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     void *d_tmp = dev.get<char>(scan_bytes);
     if (!d_slot || !d_istail || !d_tailpos || !d_tailptr || !d_headptr || !h_tailptr || !d_tmp)
       return fail(c, HPF_ENOMEM, "set-up arena too small (head split)");
-    CU(cudaMemcpyAsync(hp.row_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (head_tile) CU(cudaMemcpyAsync(hp.row_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemsetAsync(d_slot, 0xff, (size_t)m * 4, c->stream));
     head_slot_kernel<<<(H + 255) / 256, 256, 0, c->stream>>>(d_id_s, H, d_slot);
     head_flag_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(c->csr_idx, d_slot, nnz, d_istail);
     size_t sb = scan_bytes;
     CU(cub::DeviceScan::ExclusiveSum(d_tmp, sb, (const uint32_t *)d_istail, d_tailpos, (int64_t)(nnz + 1), c->stream));
-    head_split_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, d_y, d_slot, d_tailpos, nnz, c->tail_idx, c->tail_y, hp.idx, hp.y);
+    head_split_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, d_y, d_slot, d_tailpos, nnz, c->tail_idx, c->tail_y,
+                                                  head_tile ? hp.idx : nullptr, head_tile ? hp.y : nullptr);
     split_ptr_kernel<<<(n + 256) / 256, 256, 0, c->stream>>>(d_rowptr, d_tailpos, n, d_tailptr, d_headptr);
     c->launches += 4;
     CU(cudaMemcpyAsync(h_tailptr, d_tailptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    TRY(tile_count(c, dev, pin, d_headptr, n, &htc)); // the head is ONE tile: runs = users
+    if (head_tile) TRY(tile_count(c, dev, pin, d_headptr, n, &htc)); // the head is ONE tile: runs = users
+    if (dense_head) {
+      DensePlan &dp = c->dense;
+      dp.ntiles = (n + head::kUsers - 1) / head::kUsers;
+      dp.nhead = H;
+      const size_t n_pad = (size_t)dp.ntiles * head::kUsers;
+      TRY(ensure(c, &dp.Yw, &dp.Yw_cap, n_pad * head::kHead / 4));
+      TRY(ensure(c, &dp.head_ids, &dp.head_ids_cap, (size_t)head::kHead));
+      TRY(ensure(c, &dp.a_hi, &dp.a_hi_cap, n_pad * head::kFact));
+      TRY(ensure(c, &dp.a_lo, &dp.a_lo_cap, n_pad * head::kFact));
+      TRY(ensure(c, &dp.b_hi, &dp.b_hi_cap, (size_t)head::kHead * head::kFact));
+      TRY(ensure(c, &dp.b_lo, &dp.b_lo_cap, (size_t)head::kHead * head::kFact));
+      TRY(ensure(c, &dp.dB_part, &dp.dB_part_cap, (size_t)std::min<uint32_t>(dp.ntiles, (uint32_t)c->sm_count) * head::kHead * head::kFact));
+      CU(cudaMemsetAsync(dp.Yw, 0, n_pad * head::kHead, c->stream));
+      CU(cudaMemsetAsync(dp.head_ids, 0xff, (size_t)head::kHead * 4, c->stream));
+      CU(cudaMemcpyAsync(dp.head_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, dp.Yw);
+      c->launches++;
+      if (!make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) ||
+          !make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers) ||
+          !make_bf16_map(&dp.map_b_hi, dp.b_hi, head::kHead, head::kFact, head::kHead) ||
+          !make_bf16_map(&dp.map_b_lo, dp.b_lo, head::kHead, head::kFact, head::kHead))
+        return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the dense head operands");
+    }
   }
   // the item-side host work list (gather mode) can be built while the device works on stage 2
   if (!item_tile && !try_item_tile) { /* h_run arrived with stage 1 */
-    TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw));
+    TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw, skip_ptr));
   }
-  if (!head_tile) { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
+  if (!split_head) { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
     TRY(orient_device(c, dev, pin, nnz, d_rowof, c->csr_idx, d_y, true, n, m, 0, true, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
                       &c->upass_y_cap, cub_bytes, &uo));
     if (uo.from_host_rowptr) TRY(build_worklist_host(c, pin, n, row_ptr, 1, &uw));
@@ -1155,14 +1275,18 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   tr.mark("stage 2: work lists, split");
 
   // ================= stage 3: remaining host work lists, head work list, uploads =================
-  if (!item_tile && try_item_tile) TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw));
-  if (head_tile) {
+  if (!item_tile && try_item_tile) TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw, skip_ptr));
+  if (split_head) {
     const uint64_t ntail = h_tailptr[n];
-    const uint32_t head_nsegs = htc.h_last[0] + htc.h_last[1];
-    TRY(tile_emit(c, c->dev_arena2, d_headptr, htc, n, 1, head_nsegs, &c->head_tile));
-    c->head_tile.on = true; c->head_tile.nnz = nnz - ntail; c->head_tile.tile0_count = H;
-    c->head_tile.has_y = y != nullptr;
-    c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
+    if (head_tile) {
+      const uint32_t head_nsegs = htc.h_last[0] + htc.h_last[1];
+      TRY(tile_emit(c, c->dev_arena2, d_headptr, htc, n, 1, head_nsegs, &c->head_tile));
+      c->head_tile.on = true; c->head_tile.nnz = nnz - ntail; c->head_tile.tile0_count = H;
+      c->head_tile.has_y = y != nullptr;
+      c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
+    } else {
+      c->dense.on = true;
+    }
     // tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
     uint32_t *d_tailrow = nullptr;
     if (tiles_for(c, m, n, ntail) > 1 && ntail > 0) {
@@ -1433,14 +1557,8 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
       if (excl_ptr[a + 1] < excl_ptr[a]) return fail(c, HPF_EINVAL, "excl_ptr not monotone at %u", a);
     if (nex > 0 && !excl_idx) return fail(c, HPF_EINVAL, "excl_idx is null");
   }
-  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  if (!encode) {
-    cudaDriverEntryPointQueryResult qres;
-    void *fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-      return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  }
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensormap_encoder();
+  if (!encode) return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const uint32_t Kext = c->K + (c->bias ? 2u : 0u);
   const uint32_t Kpad = (Kext + topk::kBlockK - 1) / topk::kBlockK * topk::kBlockK;
   const uint32_t m_pad = (m + topk::kTileN - 1) / topk::kTileN * topk::kTileN;
@@ -1658,7 +1776,7 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
   out->last_topn_ms = c->last_topn_ms;
   out->tile_rows = c->tile_rows;
   out->item_tiles = c->item_tile.on ? c->item_tile.ntiles : 0;
-  out->head_nnz = c->head_tile.on ? c->head_tile.nnz : 0;
+  out->head_nnz = c->head_tile.on ? c->head_tile.nnz : (c->dense.on ? c->dense.head_nnz : 0);
   out->tile_segments = (uint64_t)(c->item_tile.on ? c->item_tile.nsegs : 0) + (c->head_tile.on ? c->head_tile.nsegs : 0);
   return 0;
 }

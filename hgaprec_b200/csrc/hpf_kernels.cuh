@@ -565,7 +565,7 @@ __global__ void head_split_kernel(const uint32_t *col, const uint8_t *y, const u
   if (sl == 0xffffffffu) {
     tail_idx[tp] = cc;
     if (y) tail_y[tp] = y[j];
-  } else {
+  } else if (head_idx != nullptr) { // the dense head keeps no list
     const uint64_t hp = j - tp;
     head_idx[hp] = sl;
     if (y) head_y[hp] = y[j];

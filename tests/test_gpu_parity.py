@@ -151,6 +151,26 @@ def test_l2_tiled_orderings_match_oracle(monkeypatch, flags, tile_kb):
     assert st["slow_path_nnz"] == 0
 
 
+@pytest.mark.parametrize("dense", ["1", "0"])
+@pytest.mark.parametrize("name,n,m,nnz,k,flags,binary", [
+    ("hier K=100", 3000, 1500, 200000, 100, H.HIER, False),
+    ("bpf K=33 fewer items than head slots", 700, 90, 20000, 33, 0, False),
+    ("hier binary K=128", 1000, 400, 60000, 128, H.HIER | H.BINARY, True),
+    ("bpf jacobi-less K=5, users not a multiple of 128", 517, 300, 15000, 5, 0, False),
+])
+def test_dense_head_matches_oracle_and_gather_plan(monkeypatch, dense, name, n, m, nnz, k, flags, binary):
+    """The tcgen05 dense head (forced on / off) against the oracle: three iterations, duplicates included."""
+    monkeypatch.setenv("HPF_DENSE_HEAD", dense)
+    d, s = _oracle_case(n, m, nnz, k, flags, seed=53, binary=binary)
+    rp, ci, y = d["row_ptr"].astype(np.int64), d["col_idx"].copy(), d["y"]
+    ci[rp[3] + 1] = ci[rp[3]]  # a repeated (user, item) entry: walked twice by the reference
+    want = s.copy().iterate(rp, ci, y, 3, nthreads=8)
+    got, st = run_engine(s, rp, ci, y, 3)
+    assert (st["head_nnz"] > 0) == (dense == "1") and st["slow_path_nnz"] == 0
+    bad = util.compare_states(got, want, rel=6e-5, elog_abs=6e-5)
+    assert not bad, (name, bad)
+
+
 def test_no_ratings_at_all_and_y_null():
     n, m, k = 10, 12, 4
     s = O.OracleState(n, m, k, 0).init(2)
@@ -191,12 +211,14 @@ def test_exact_fallback_when_products_underflow():
     assert not util.compare_states(got2, want, rel=6e-5, elog_abs=6e-5)
 
 
-def test_default_plan_is_bitwise_deterministic():
-    """The default plan (gather kernel on both sides, tile sweeps off) sums in a fixed order."""
-    d, s = _oracle_case(2000, 700, 90000, 100, H.HIER | H.BIAS, seed=8)
+@pytest.mark.parametrize("flags,dense", [(H.HIER | H.BIAS, False), (H.HIER, True), (0, True)])
+def test_default_plan_is_bitwise_deterministic(flags, dense):
+    """The default plan (gather kernel for the tail, dense tcgen05 head where it applies: no bias, K <= 128)
+    sums in a fixed order."""
+    d, s = _oracle_case(2000, 700, 90000, 100, flags, seed=8)
     a, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
     b, _ = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
-    assert st["item_tiles"] == 0 and st["head_nnz"] == 0
+    assert st["item_tiles"] == 0 and (st["head_nnz"] > 0) == dense
     for gname in util.groups(a):
         for f in O.FIELDS:
             np.testing.assert_array_equal(a.p[gname][f], b.p[gname][f])
@@ -204,6 +226,7 @@ def test_default_plan_is_bitwise_deterministic():
 
 def test_tile_sweep_runs_agree_to_summation_order(monkeypatch):
     """The tile sweeps add partial sums with fp32 reductions whose order is not fixed."""
+    monkeypatch.setenv("HPF_DENSE_HEAD", "0")
     monkeypatch.setenv("HPF_ITEM_TILE", "1")
     monkeypatch.setenv("HPF_HEAD_TILE", "1")
     d, s = _oracle_case(2000, 700, 90000, 100, H.HIER | H.BIAS, seed=8)
@@ -219,6 +242,7 @@ def test_tile_sweep_runs_agree_to_summation_order(monkeypatch):
 def test_every_sweep_plan_matches_oracle(monkeypatch, flags, item_tile, head_tile, tile_rows):
     """gather-only, tile sweeps forced on one side or both, small forced tiles (many
     user blocks, head smaller than the item set, rows split over segments)."""
+    monkeypatch.setenv("HPF_DENSE_HEAD", "0")
     monkeypatch.setenv("HPF_ITEM_TILE", item_tile)
     monkeypatch.setenv("HPF_HEAD_TILE", head_tile)
     monkeypatch.setenv("HPF_SEG_LEN", "64")
