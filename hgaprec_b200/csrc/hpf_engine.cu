@@ -129,6 +129,7 @@ struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
   float *dB_part = nullptr; size_t dB_part_cap = 0;   // per-CTA partial sums of the head items' T_beta rows
   uint32_t ntiles = 0, nhead = 0;
   uint64_t head_nnz = 0;
+  bool a_dirty = true; // the split copy of A does not match A (after hpf_set_state / a new plan); update_kernel keeps it fresh
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
 };
 
@@ -184,7 +185,7 @@ struct hpf_ctx {
   Arena dev_arena, dev_arena2, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
   DensePlan dense;               // the most popular items as a dense block on the tensor cores
-  int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 25 % of the nonzeros), 0 off, 1 forced
+  int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 15 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
   uint32_t tile_rows = 0; size_t tile_smem = 0;
   int item_tile_mode = 0, head_tile_mode = 0; // 0 off (default: measured slower than the gather kernel), 1 forced, -1 auto
@@ -455,6 +456,9 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   a.bias_prior_shape = (float)s.bias_prior_shape;
   a.bias_rate_total = (float)(s.bias_prior_rate + bias_count);
   a.colsum_partial = s.colsum_partial;
+  if (&s == &c->th && c->dense.on && !c->dense.a_dirty) { // keep the dense head's operand copy of A in step
+    a.split_hi = c->dense.a_hi; a.split_lo = c->dense.a_lo; a.split_ld = head::kFact;
+  }
   const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
   update_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(a);
   c->launches++;
@@ -842,7 +846,11 @@ int launch_dense_head(hpf_ctx *c)
   DensePlan &d = c->dense;
   if (!d.on) return 0;
   const uint32_t n = c->th.R, n_pad = d.ntiles * head::kUsers;
-  topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->K, nullptr, 0, nullptr, n, n_pad, head::kFact, d.a_hi, d.a_lo);
+  if (d.a_dirty) {
+    topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->K, nullptr, 0, nullptr, n, n_pad, head::kFact, d.a_hi, d.a_lo);
+    c->launches++;
+    d.a_dirty = false;
+  }
   topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, d.head_ids, d.nhead, head::kHead, head::kFact, d.b_hi, d.b_lo);
   head::HeadArgs a;
   a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
@@ -854,7 +862,7 @@ int launch_dense_head(hpf_ctx *c)
   const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
   head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi, d.map_b_lo, a);
   head::head_reduce_kernel<<<d.nhead, 128, 0, c->stream>>>(d.dB_part, grid, d.head_ids, c->Kp, c->ld, c->be.T);
-  c->launches += 4;
+  c->launches += 3;
   CU(cudaGetLastError());
   return 0;
 }
@@ -1180,7 +1188,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     H = std::min<uint32_t>(head::kHead, m);
     uint64_t head_nnz = 0;
     for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
-    dense_head = c->dense_head_mode == 1 || (double)head_nnz >= 0.25 * (double)nnz;
+    dense_head = c->dense_head_mode == 1 || (double)head_nnz >= 0.15 * (double)nnz;
     if (dense_head) {
       c->dense.head_nnz = head_nnz;
       skip_item.assign(m, 0);
@@ -1286,6 +1294,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
       c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
     } else {
       c->dense.on = true;
+      c->dense.a_dirty = true;
     }
     // tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
     uint32_t *d_tailrow = nullptr;
@@ -1342,6 +1351,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
     if ((rc = refresh_colsum(c, s))) break;
     s.have_state = true;
     c->aux_dirty = true;
+    if (theta_side) c->dense.a_dirty = true;
     if (theta_side) c->th_colsum_global = false;
     break;
   }

@@ -41,7 +41,8 @@ using namespace topk; // smem_u32, mbar_*, tma_load_2d, tc_*
 constexpr int kHead = 128;     // head items  (N of MMA 1, K of MMA 2, M of MMA 3)
 constexpr int kUsers = 128;    // users per tile (M of MMA 1/2, K of MMA 3)
 constexpr int kFact = 128;     // padded factor dimension (K of MMA 1, N of MMA 2/3)
-constexpr int kThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each taking half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
 constexpr uint32_t kBlk = 16384;            // one [128 rows x 64 bf16] swizzled block
 constexpr uint32_t kOperand = 2 * kBlk;     // one 128 x 128 bf16 operand (hi or lo)
 constexpr uint32_t kSmemA = 0, kSmemB = 2 * kOperand, kSmemP = 4 * kOperand, kSmemBar = 6 * kOperand;
@@ -114,7 +115,7 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     mbar_init(bar_a_full, 1); mbar_init(bar_a_empty, 1); mbar_init(bar_b_full, 1);
-    mbar_init(bar_z_full, 1); mbar_init(bar_p_full, 128); mbar_init(bar_o_full, 1); mbar_init(bar_o_empty, 128);
+    mbar_init(bar_z_full, 1); mbar_init(bar_p_full, 32 * kEpiWarps); mbar_init(bar_o_full, 1); mbar_init(bar_o_empty, 32 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -194,8 +195,9 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: one thread per user row =====
-    const int q = warp & 3;
+    // ===== epilogue: two threads per user row (one per half of the columns) =====
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;       // 0: columns 0-63, 1: columns 64-127
     const uint32_t r = (uint32_t)(q * 32 + lane);          // row inside the tile == TMEM lane
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -206,7 +208,7 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       mbar_wait(bar_z_full, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (uint32_t c = 0; c < kHead / 32; ++c) {
+      for (uint32_t c = half * 2u; c < half * 2u + 2u; ++c) {
         uint32_t z[32];
         tc_ld32(tm_z + lane_addr + c * 32u, z);
         const uint4 y0 = __ldg(reinterpret_cast<const uint4 *>(yrow + c * 32u));
@@ -250,11 +252,11 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       tc_fence_after();
       float *trow = a.T_theta + (size_t)u * a.ld;
 #pragma unroll 1
-      for (uint32_t c = 0; c * 32u < a.K; ++c) {
+      for (uint32_t c = half * 2u; c < half * 2u + 2u; ++c) {
         uint32_t o[32];
         tc_ld32(tm_o + lane_addr + c * 32u, o);
         tc_wait_ld();
-        if (u < a.n) {
+        if (u < a.n && c * 32u < a.K) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const uint32_t k = c * 32u + j;
@@ -274,7 +276,7 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     {
       float *brow = a.dB_part + ((size_t)blockIdx.x * kHead + r) * kFact;
 #pragma unroll 1
-      for (uint32_t c = 0; c < kFact / 32; ++c) {
+      for (uint32_t c = half * 2u; c < half * 2u + 2u; ++c) {
         uint32_t d[32];
         if (my_tiles > 0) { // the last bar_o_full wait above already covers the final MMA 3
           tc_ld32(tm_db + lane_addr + c * 32u, d);

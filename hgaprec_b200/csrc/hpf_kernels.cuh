@@ -17,6 +17,7 @@
 // log-domain fallback (sweep_slow_path) that adds y*phi straight into a side
 // buffer.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -658,6 +659,9 @@ struct UpdateArgs {
   float2 *aux;
   float bias_prior_shape, bias_rate_total; // rate prior + (m or n_global)
   float *colsum_partial;               // [gridDim.x x Kp]
+  // dense-head plan: the split-bf16 copy of A (row stride split_ld) that head_kernel reads by TMA
+  __nv_bfloat16 *split_hi, *split_lo;
+  uint32_t split_ld;
 };
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -720,8 +724,15 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
     }
     mx = warp_max(mx);
     rowsum = warp_sum(rowsum);
-    for (uint32_t k = lane; k < a.Kp; k += 32)
-      a.A[base + k] = k < a.K ? expf(a.Elog[base + k] - mx) : 0.f;
+    for (uint32_t k = lane; k < a.Kp; k += 32) {
+      const float av = k < a.K ? expf(a.Elog[base + k] - mx) : 0.f;
+      a.A[base + k] = av;
+      if (a.split_hi != nullptr) { // x = hi + lo in bf16 (representation error 2^-18)
+        const __nv_bfloat16 h = __float2bfloat16_rn(av);
+        a.split_hi[(size_t)r * a.split_ld + k] = h;
+        a.split_lo[(size_t)r * a.split_ld + k] = __float2bfloat16_rn(av - __bfloat162float(h));
+      }
+    }
     if (lane == 0) {
       a.shift[r] = mx;
       if (a.hier) {
