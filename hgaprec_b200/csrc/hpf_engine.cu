@@ -127,11 +127,12 @@ struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
   __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
   size_t a_hi_cap = 0, a_lo_cap = 0, b_hi_cap = 0, b_lo_cap = 0;
   float *dB_part = nullptr; size_t dB_part_cap = 0;   // per-CTA partial sums of the head items' T_beta rows
-  uint32_t ntiles = 0, nhead = 0;
+  uint32_t ntiles = 0, nhead = 0, nblocks = 0; // nhead items in nblocks blocks of 128 (by descending popularity)
   uint64_t head_nnz = 0;
   bool a_dirty = true; // the split copy of A does not match A (after hpf_set_state / a new plan); update_kernel keeps it fresh
-  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi[4], map_b_lo[4];
 };
+constexpr uint32_t kMaxHeadBlocks = 4;
 
 struct WorkList {       // segments of one orientation, sorted by descending length
   uint4 *seg = nullptr;
@@ -185,6 +186,7 @@ struct hpf_ctx {
   Arena dev_arena, dev_arena2, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
   DensePlan dense;               // the most popular items as a dense block on the tensor cores
+  double dense_block_share = 0.06; // HPF_DENSE_BLOCK_SHARE: minimum share of the nonzeros for a 2nd..4th head block
   int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 15 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
   uint32_t tile_rows = 0; size_t tile_smem = 0;
@@ -851,18 +853,24 @@ int launch_dense_head(hpf_ctx *c)
     c->launches++;
     d.a_dirty = false;
   }
-  topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, d.head_ids, d.nhead, head::kHead, head::kFact, d.b_hi, d.b_lo);
-  head::HeadArgs a;
-  a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
-  a.Y = reinterpret_cast<const uint8_t *>(d.Yw); a.head_ids = d.head_ids;
-  a.T_theta = c->th.T; a.dB_part = d.dB_part;
-  a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
-  a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
   CU(cudaFuncSetAttribute(head::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
   const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
-  head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi, d.map_b_lo, a);
-  head::head_reduce_kernel<<<d.nhead, 128, 0, c->stream>>>(d.dB_part, grid, d.head_ids, c->Kp, c->ld, c->be.T);
-  c->launches += 3;
+  for (uint32_t b = 0; b < d.nblocks; ++b) { // one pass over the users per block of 128 head items
+    const uint32_t nh = std::min<uint32_t>(head::kHead, d.nhead - b * head::kHead);
+    const size_t boff = (size_t)b * head::kHead * head::kFact;
+    const uint32_t *ids = d.head_ids + (size_t)b * head::kHead;
+    float *part = d.dB_part + (size_t)b * grid * head::kHead * head::kFact;
+    topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, ids, nh, head::kHead, head::kFact, d.b_hi + boff, d.b_lo + boff);
+    head::HeadArgs a;
+    a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
+    a.Y = reinterpret_cast<const uint8_t *>(d.Yw) + (size_t)b * n_pad * head::kHead; a.head_ids = ids;
+    a.T_theta = c->th.T; a.dB_part = part;
+    a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
+    a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
+    head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
+    head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T);
+    c->launches += 3;
+  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -1005,6 +1013,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     if (const char *e = getenv("HPF_ITEM_TILE")) n->item_tile_mode = atoi(e);
     if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
     if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
+    if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
     if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
       const uint32_t v = (uint32_t)atoi(e);
       if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }
@@ -1156,9 +1165,9 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     CU(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const uint32_t *)d_degkey, d_degkey_s, (const uint32_t *)d_id, d_id_s, (int64_t)m, 0, 32, c->stream));
     c->launches += 2;
     CU(cudaMemcpyAsync(h_degkey, d_degkey_s, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
-    h_headid = pin.get<uint32_t>(head::kHead);
+    h_headid = pin.get<uint32_t>(kMaxHeadBlocks * head::kHead);
     if (!h_headid) return fail(c, HPF_ENOMEM, "pinned arena too small");
-    CU(cudaMemcpyAsync(h_headid, d_id_s, (size_t)std::min<uint32_t>(m, head::kHead) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_headid, d_id_s, (size_t)std::min<uint32_t>(m, kMaxHeadBlocks * head::kHead) * 4, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -1185,12 +1194,24 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   bool dense_head = false;
   std::vector<uint8_t> skip_item;
   if (try_dense && !head_tile) {
-    H = std::min<uint32_t>(head::kHead, m);
+    // blocks of 128 items by descending popularity: the first must carry >= 15 % of the nonzeros, every further
+    // one >= 6 % (a block costs one dense pass over all users whatever its density; measured break-even ~6 %)
     uint64_t head_nnz = 0;
-    for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
-    dense_head = c->dense_head_mode == 1 || (double)head_nnz >= 0.15 * (double)nnz;
+    uint32_t nblk = 0;
+    for (uint32_t b = 0; b < kMaxHeadBlocks && b * head::kHead < m; ++b) {
+      uint64_t blk = 0;
+      for (uint32_t r = b * head::kHead; r < std::min<uint32_t>((b + 1) * head::kHead, m); ++r) blk += 0xffffffffu - h_degkey[r];
+      const bool take = b == 0 ? (c->dense_head_mode == 1 || (double)blk >= 0.15 * (double)nnz)
+                               : ((double)blk >= c->dense_block_share * (double)nnz);
+      if (!take) break;
+      head_nnz += blk;
+      nblk = b + 1;
+    }
+    dense_head = nblk > 0;
     if (dense_head) {
+      H = std::min<uint32_t>(nblk * head::kHead, m);
       c->dense.head_nnz = head_nnz;
+      c->dense.nblocks = nblk;
       skip_item.assign(m, 0);
       for (uint32_t r = 0; r < H; ++r) skip_item[h_headid[r]] = 1; // the item pass has no rows for head items
     }
@@ -1250,23 +1271,25 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
       dp.ntiles = (n + head::kUsers - 1) / head::kUsers;
       dp.nhead = H;
       const size_t n_pad = (size_t)dp.ntiles * head::kUsers;
-      TRY(ensure(c, &dp.Yw, &dp.Yw_cap, n_pad * head::kHead / 4));
-      TRY(ensure(c, &dp.head_ids, &dp.head_ids_cap, (size_t)head::kHead));
+      const size_t NB = dp.nblocks;
+      TRY(ensure(c, &dp.Yw, &dp.Yw_cap, NB * n_pad * head::kHead / 4));
+      TRY(ensure(c, &dp.head_ids, &dp.head_ids_cap, NB * head::kHead));
       TRY(ensure(c, &dp.a_hi, &dp.a_hi_cap, n_pad * head::kFact));
       TRY(ensure(c, &dp.a_lo, &dp.a_lo_cap, n_pad * head::kFact));
-      TRY(ensure(c, &dp.b_hi, &dp.b_hi_cap, (size_t)head::kHead * head::kFact));
-      TRY(ensure(c, &dp.b_lo, &dp.b_lo_cap, (size_t)head::kHead * head::kFact));
-      TRY(ensure(c, &dp.dB_part, &dp.dB_part_cap, (size_t)std::min<uint32_t>(dp.ntiles, (uint32_t)c->sm_count) * head::kHead * head::kFact));
-      CU(cudaMemsetAsync(dp.Yw, 0, n_pad * head::kHead, c->stream));
-      CU(cudaMemsetAsync(dp.head_ids, 0xff, (size_t)head::kHead * 4, c->stream));
+      TRY(ensure(c, &dp.b_hi, &dp.b_hi_cap, NB * head::kHead * head::kFact));
+      TRY(ensure(c, &dp.b_lo, &dp.b_lo_cap, NB * head::kHead * head::kFact));
+      TRY(ensure(c, &dp.dB_part, &dp.dB_part_cap, NB * std::min<uint32_t>(dp.ntiles, (uint32_t)c->sm_count) * head::kHead * head::kFact));
+      CU(cudaMemsetAsync(dp.Yw, 0, NB * n_pad * head::kHead, c->stream));
+      CU(cudaMemsetAsync(dp.head_ids, 0xff, NB * head::kHead * 4, c->stream));
       CU(cudaMemcpyAsync(dp.head_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
-      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, dp.Yw);
+      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, n_pad * head::kHead, dp.Yw);
       c->launches++;
-      if (!make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) ||
-          !make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers) ||
-          !make_bf16_map(&dp.map_b_hi, dp.b_hi, head::kHead, head::kFact, head::kHead) ||
-          !make_bf16_map(&dp.map_b_lo, dp.b_lo, head::kHead, head::kFact, head::kHead))
-        return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the dense head operands");
+      bool maps_ok = make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) &&
+                     make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers);
+      for (size_t b = 0; b < NB; ++b)
+        maps_ok = maps_ok && make_bf16_map(&dp.map_b_hi[b], dp.b_hi + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead) &&
+                  make_bf16_map(&dp.map_b_lo[b], dp.b_lo + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead);
+      if (!maps_ok) return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the dense head operands");
     }
   }
   // the item-side host work list (gather mode) can be built while the device works on stage 2

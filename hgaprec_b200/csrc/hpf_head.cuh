@@ -304,15 +304,16 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 // ---- set-up / per-iteration helpers ---------------------------------------------
 // dense ratings of the head block: Y[u * 128 + slot] += y for every nonzero of a head item
 // (a repeated (user, item) line adds up: same Z, so the contributions add as in the reference's walk)
+// slot s = block * 128 + position; every block has its own [n_pad x 128] byte matrix (block_stride bytes apart)
 __global__ void dense_y_kernel(const uint32_t *row_of, const uint32_t *col, const uint8_t *y, const uint32_t *slot_of, uint64_t nnz,
-                               uint32_t *Yw)
+                               size_t block_stride, uint32_t *Yw)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
   const uint32_t s = slot_of[col[j]];
   if (s == 0xffffffffu) return;
   const uint32_t yv = y ? y[j] : 1u;
-  const size_t e = (size_t)row_of[j] * kHead + s;
+  const size_t e = (size_t)(s / kHead) * block_stride + (size_t)row_of[j] * kHead + (s % kHead);
   atomicAdd(Yw + (e >> 2), yv << ((e & 3u) * 8u));
 }
 

@@ -161,6 +161,7 @@ def test_l2_tiled_orderings_match_oracle(monkeypatch, flags, tile_kb):
 def test_dense_head_matches_oracle_and_gather_plan(monkeypatch, dense, name, n, m, nnz, k, flags, binary):
     """The tcgen05 dense head (forced on / off) against the oracle: three iterations, duplicates included."""
     monkeypatch.setenv("HPF_DENSE_HEAD", dense)
+    monkeypatch.setenv("HPF_DENSE_BLOCK_SHARE", "0")  # as many 128-item head blocks as there are items (up to 4)
     d, s = _oracle_case(n, m, nnz, k, flags, seed=53, binary=binary)
     rp, ci, y = d["row_ptr"].astype(np.int64), d["col_idx"].copy(), d["y"]
     ci[rp[3] + 1] = ci[rp[3]]  # a repeated (user, item) entry: walked twice by the reference
