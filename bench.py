@@ -288,20 +288,20 @@ def main():
     # ---- per-kernel device times (live, CUDA events on the launching stream)
     prof = eng.iterate_profiled(5)
     peak, peak_src = measured_peaks()
-    sweep_bytes = sweep_launch_bytes(n, nnz, k, has_y) + sweep_launch_bytes(m, nnz, k, has_y)
-    sweep_ms = prof["sweep_user_ms"] + prof["sweep_item_ms"]
+    # dominant kernel: hpf::sweep_kernel, two launches per iteration (user pass, item pass).  When the dense
+    # tcgen05 head is on, the nonzeros of the head items are not in these launches (they run in head_kernel).
+    stats0 = eng.stats()
+    head_nnz = int(stats0["head_nnz"]) if not stats0["item_tiles"] else 0
+    gather_nnz = nnz - head_nnz
+    sweep_bytes = sweep_launch_bytes(n, gather_nnz, k, has_y) + sweep_launch_bytes(m, gather_nnz, k, has_y)
+    sweep_ms = prof["sweep_user_ms"] - prof["sweep_user_head_ms"] + prof["sweep_item_ms"]
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "sweep_dram_bytes.json")
-    if os.path.exists(tfile):
-        try:
-            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
     roofline = {"bound": "hbm", "kernel": "hpf::sweep_kernel (2 launches / iteration: user pass + item pass)",
                 "note": "algorithmic bytes count a gathered factor row once per nonzero (SURVEY 8d); the rows are L2-resident at "
                         "this size, so frac > 1 is expected and the binding limit is the L2->SM gather rate (see DESIGN.md 5)",
-                "l2_gather_TBps": (2 * nnz * (4 * ((k + 3) // 4 * 4) + 5)) / (sweep_ms * 1e-3) / 1e12,
+                "l2_gather_TBps": (2 * gather_nnz * (4 * ((k + 3) // 4 * 4) + 5)) / (sweep_ms * 1e-3) / 1e12,
+                "gather_nnz_per_launch": gather_nnz, "dense_head_nnz": head_nnz,
+                "dense_head_ms": prof["sweep_user_head_ms"],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes / 2,
@@ -356,8 +356,10 @@ def main():
                            "l2_policy": "inputs larger than L2 (ratings %.0f MB + factor rows %.0f MB per GPU vs 126 MB L2)"
                                         % ((2 * nnz * 5) / 1e6, (n + m) * k * 4 * 2 / 1e6),
                            "sweep_group": stats["sweep_group"], "sweep_vec": stats["sweep_vec"],
-                           "sweep_plan": "gather kernel on both passes" if not (stats["item_tiles"] or stats["head_nnz"]) else
-                                         "tile sweeps: item_tiles=%d head_nnz=%d" % (stats["item_tiles"], stats["head_nnz"]),
+                           "sweep_plan": ("gather kernel on both passes" if not (stats["item_tiles"] or stats["head_nnz"]) else
+                                          "gather kernel for the tail + dense tcgen05 head (%d nonzeros of the most popular items)"
+                                          % stats["head_nnz"] if not stats["item_tiles"] else
+                                          "tile sweeps: item_tiles=%d head_nnz=%d" % (stats["item_tiles"], stats["head_nnz"])),
                            "state_init": "random Gamma(0.3+U,0.3+U) start (reference initialize() law), synthetic"},
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "clocks": clocks, "wall_s_timed_region": t_wall,
