@@ -296,6 +296,13 @@ def main():
     sweep_bytes = sweep_launch_bytes(n, gather_nnz, k, has_y) + sweep_launch_bytes(m, gather_nnz, k, has_y)
     sweep_ms = prof["sweep_user_ms"] - prof["sweep_user_head_ms"] + prof["sweep_item_ms"]
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "sweep_dram_bytes.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": "hpf::sweep_kernel (2 launches / iteration: user pass + item pass)",
                 "note": "algorithmic bytes count a gathered factor row once per nonzero (SURVEY 8d); the rows are L2-resident at "
                         "this size, so frac > 1 is expected and the binding limit is the L2->SM gather rate (see DESIGN.md 5)",

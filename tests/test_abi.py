@@ -64,3 +64,29 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in txt.replace("hpf_oracle_not", ""), "%s mentions the oracle" % fn
+
+
+def test_bench_and_entry_scripts_have_no_undefined_names():
+    """bench.py only runs on the GPU box; catch typos (a name used but never bound) here."""
+    import ast
+    import builtins
+    for script in ("bench.py", "__graft_entry__.py"):
+        tree = ast.parse(open(os.path.join(ROOT, script)).read())
+        bound = set(dir(builtins)) | {"__file__", "__name__"}
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Name) and isinstance(node.ctx, (ast.Store, ast.Del)):
+                bound.add(node.id)
+            elif isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+                bound.add(node.name)
+                if isinstance(node, ast.FunctionDef):
+                    a = node.args
+                    bound.update(x.arg for x in a.args + a.kwonlyargs + a.posonlyargs)
+                    bound.update(x.arg for x in (a.vararg, a.kwarg) if x)
+            elif isinstance(node, ast.Lambda):
+                bound.update(x.arg for x in node.args.args)
+            elif isinstance(node, (ast.Import, ast.ImportFrom)):
+                bound.update((x.asname or x.name).split(".")[0] for x in node.names)
+            elif isinstance(node, ast.ExceptHandler) and node.name:
+                bound.add(node.name)
+        used = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+        assert not sorted(used - bound), (script, sorted(used - bound))
