@@ -150,7 +150,7 @@ template <int G>
 __device__ __forceinline__ uint32_t group_mask(int lane)
 {
   if (G == 32) return 0xffffffffu;
-  return ((1u << G) - 1u) << (lane & ~(G - 1));
+  return ((1u << (G & 31)) - 1u) << (lane & ~(G - 1));
 }
 
 // Exact log-domain phi for one nonzero (called when Z left the fp32 range):

@@ -403,8 +403,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       ex = a.excl_sorted + e0;
       exlen = (uint32_t)(e1 - e0);
     }
-    unsigned long long tau = 0ull;                 // keys <= tau can no longer make the top-n
-    uint32_t tau_hi = live ? 0u : 0xffffffffu;
+    uint32_t tau_hi = live ? 0u : 0xffffffffu;     // score word of the row's threshold: smaller scores cannot make the top-n
     uint32_t cnt = 0;
     uint32_t excur = 0;                            // cursor into the (ascending) exclusion list
     for (uint32_t j = 0; j < a.ntiles_n; ++j) {
@@ -463,7 +462,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const unsigned long long thr = warp_select(rb, rcnt, keep, lane);
         if (lane == src) {
           cnt = keep;
-          if (rcnt >= a.topn) { tau = thr; tau_hi = (uint32_t)(thr >> 32); }
+          if (rcnt >= a.topn) tau_hi = (uint32_t)(thr >> 32);
         }
       }
     }
