@@ -273,7 +273,7 @@ void HGAPRec::exclusions_of(const std::vector<uint32_t> &users, std::vector<uint
     const uint32_t u = users[a];
     const std::vector<uint32_t> &tr = ratings_.items_of(u);
     for (size_t j = 0; j < tr.size(); ++j)
-      if (ratings_.r(u, tr[j]) > 0) idx->push_back(tr[j]);
+      if (ratings_.value_at(u, j) > 0) idx->push_back(tr[j]);
     for (HeldoutMap::const_iterator it = validation_map_.lower_bound(Pair(u, 0)); it != validation_map_.end() && it->first.first == u; ++it)
       idx->push_back(it->first.second);
     (*ptr)[a + 1] = idx->size();
@@ -365,7 +365,7 @@ void HGAPRec::compute_itemrank(bool final)
     std::vector<uint32_t> tr;
     const std::vector<uint32_t> &it = ratings_.items_of(u);
     for (size_t j = 0; j < it.size(); ++j)
-      if (ratings_.r(u, it[j]) > 0) tr.push_back(it[j]);
+      if (ratings_.value_at(u, j) > 0) tr.push_back(it[j]);
     std::sort(tr.begin(), tr.end());
     const uint32_t nranked = m_ - (uint32_t)(std::unique(tr.begin(), tr.end()) - tr.begin());
     // the reference walks the list top-down: emit the hits by ascending position
@@ -378,7 +378,7 @@ void HGAPRec::compute_itemrank(bool final)
       const uint64_t q = order[o].second;
       const uint32_t j = order[o].first;
       ntestitems++;
-      fprintf(f, "%d\t%d\t%.5f\t%d\t%d\n", u, qidx[q], pred[q], j, (int)ratings_.users_of(qidx[q]).size());
+      fprintf(f, "%d\t%d\t%.5f\t%d\t%d\n", u, qidx[q], pred[q], j, (int)ratings_.item_degree(qidx[q]));
       rank_ui += (j + 1);
       reciprocal_rank_ui += 1 / (j + 1); // integer division, as in the reference (1683)
     }

@@ -5,13 +5,26 @@
 
 namespace hpfhost {
 
-namespace {
-// one "%u\t%u\t%u" record per call; false at end of input
-bool next_triple(FILE *f, uint32_t *a, uint32_t *b, uint32_t *c)
+// one unsigned decimal (strtoul-like: optional sign, wraps modulo 2^32); false at end of input
+bool TripleReader::number(uint32_t *out)
 {
-  return fscanf(f, "%u %u %u", a, b, c) == 3;
+  int ch = get();
+  while (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r') ch = get();
+  if (ch < 0) return false;
+  bool neg = false;
+  if (ch == '+' || ch == '-') {
+    neg = ch == '-';
+    ch = get();
+  }
+  if (ch < '0' || ch > '9') return false;
+  uint32_t v = 0;
+  while (ch >= '0' && ch <= '9') {
+    v = v * 10u + (uint32_t)(ch - '0');
+    ch = get();
+  }
+  *out = neg ? 0u - v : v;
+  return true;
 }
-} // namespace
 
 bool Ratings::read_train(const std::string &dir, std::string *err)
 {
@@ -21,34 +34,66 @@ bool Ratings::read_train(const std::string &dir, std::string *err)
     *err = "cannot open file " + path + ": " + strerror(errno);
     return false;
   }
+  TripleReader rd(f);
   uint32_t uid, iid, rating;
-  while (next_triple(f, &uid, &iid, &rating)) {
-    std::unordered_map<uint32_t, uint32_t>::iterator ut = user2seq_.find(uid), it = item2seq_.find(iid);
-    if ((ut == user2seq_.end() && seq2user_.size() >= max_users_) || (it == item2seq_.end() && seq2item_.size() >= max_items_))
-      continue;
+  uint32_t last_uid = 0, last_u = 0;
+  bool have_last = false; // lines of one user usually come together: skip the map lookup
+  while (rd.next(&uid, &iid, &rating)) {
+    uint32_t u = 0, i = 0;
+    bool new_user = false, new_item = false;
+    if (have_last && uid == last_uid) u = last_u;
+    else {
+      std::unordered_map<uint32_t, uint32_t>::iterator ut = user2seq_.find(uid);
+      if (ut == user2seq_.end()) new_user = true; else u = ut->second;
+    }
+    std::unordered_map<uint32_t, uint32_t>::iterator it = item2seq_.find(iid);
+    if (it == item2seq_.end()) new_item = true; else i = it->second;
+    if ((new_user && seq2user_.size() >= max_users_) || (new_item && seq2item_.size() >= max_items_)) continue;
     if (rating_class(rating) == 0) continue;
-    uint32_t u, i;
-    if (ut == user2seq_.end()) {
+    if (new_user) {
       u = (uint32_t)seq2user_.size();
       user2seq_[uid] = u;
       seq2user_.push_back(uid);
-      user_items_.push_back(std::vector<uint32_t>());
-    } else
-      u = ut->second;
-    if (it == item2seq_.end()) {
+      items_.push_back(std::vector<uint32_t>());
+      vals_.push_back(std::vector<uint8_t>());
+    }
+    if (new_item) {
       i = (uint32_t)seq2item_.size();
       item2seq_[iid] = i;
       seq2item_.push_back(iid);
-      item_users_.push_back(std::vector<uint32_t>());
-    } else
-      i = it->second;
+    }
+    last_uid = uid; last_u = u; have_last = true;
     nratings_++;
-    value_[((uint64_t)u << 32) | i] = binary_ ? (uint8_t)1 : (uint8_t)rating;
-    user_items_[u].push_back(i);
-    item_users_[i].push_back(u);
+    items_[u].push_back(i);
+    vals_[u].push_back(binary_ ? (uint8_t)1 : (uint8_t)rating);
   }
   fclose(f);
+  finalize();
   return true;
+}
+
+void Ratings::finalize()
+{
+  const uint32_t M = m();
+  item_degree_.assign(M, 0);
+  item_total_.assign(M, 0);
+  std::vector<uint32_t> last_pos(M, 0xffffffffu); // scratch: last position of an item inside the current user
+  for (uint32_t u = 0; u < n(); ++u) {
+    std::vector<uint32_t> &v = items_[u];
+    std::vector<uint8_t> &w = vals_[u];
+    bool dup = false;
+    for (size_t j = 0; j < v.size(); ++j) {
+      if (last_pos[v[j]] != 0xffffffffu) dup = true;
+      last_pos[v[j]] = (uint32_t)j;
+    }
+    if (dup) // every occurrence reads the value of the last line (the reference's map was overwritten)
+      for (size_t j = 0; j < v.size(); ++j) w[j] = w[last_pos[v[j]]];
+    for (size_t j = 0; j < v.size(); ++j) {
+      last_pos[v[j]] = 0xffffffffu;
+      item_degree_[v[j]]++;
+      item_total_[v[j]] += w[j];
+    }
+  }
 }
 
 bool Ratings::read_heldout(const std::string &path, HeldoutMap *out, std::string *err) const
@@ -58,8 +103,9 @@ bool Ratings::read_heldout(const std::string &path, HeldoutMap *out, std::string
     *err = "cannot open file " + path + ": " + strerror(errno);
     return false;
   }
+  TripleReader rd(f);
   uint32_t uid, iid, rating;
-  while (next_triple(f, &uid, &iid, &rating)) {
+  while (rd.next(&uid, &iid, &rating)) {
     std::unordered_map<uint32_t, uint32_t>::const_iterator ut = user2seq_.find(uid), it = item2seq_.find(iid);
     if (ut == user2seq_.end() || it == item2seq_.end()) continue; // capacity is exhausted after training
     if (rating_class(rating) == 0) continue;
@@ -73,8 +119,9 @@ bool Ratings::read_test_users(const std::string &path, std::map<uint32_t, bool> 
 {
   FILE *f = fopen(path.c_str(), "r");
   if (!f) return false;
+  TripleReader rd(f);
   uint32_t uid;
-  while (fscanf(f, "%u", &uid) == 1) {
+  while (rd.number(&uid)) {
     std::unordered_map<uint32_t, uint32_t>::const_iterator ut = user2seq_.find(uid);
     if (ut != user2seq_.end()) (*out)[ut->second] = true;
   }
@@ -90,12 +137,10 @@ void Ratings::to_csr(std::vector<uint64_t> *row_ptr, std::vector<uint32_t> *col_
   col_idx->reserve(nratings_);
   y->reserve(nratings_);
   for (uint32_t u = 0; u < n(); ++u) {
-    const std::vector<uint32_t> &v = user_items_[u];
-    for (size_t j = 0; j < v.size(); ++j) {
-      col_idx->push_back(v[j]);
-      const uint32_t val = r(u, v[j]);
-      y->push_back((uint8_t)(val == 0 ? 1 : val));
-    }
+    const std::vector<uint32_t> &v = items_[u];
+    const std::vector<uint8_t> &w = vals_[u];
+    col_idx->insert(col_idx->end(), v.begin(), v.end());
+    for (size_t j = 0; j < v.size(); ++j) y->push_back((uint8_t)(w[j] == 0 ? 1 : w[j]));
     (*row_ptr)[u + 1] = col_idx->size();
   }
 }
@@ -105,22 +150,19 @@ void Ratings::write_marginals(const std::string &outdir) const
   FILE *f = fopen((outdir + "/byusers.tsv").c_str(), "w");
   if (f) {
     for (uint32_t u = 0; u < n(); ++u) {
-      const std::vector<uint32_t> &v = user_items_[u];
-      if (v.empty()) continue;
+      const std::vector<uint8_t> &w = vals_[u];
+      if (w.empty()) continue;
       uint32_t t = 0;
-      for (size_t j = 0; j < v.size(); ++j) t += r(u, v[j]);
-      fprintf(f, "%d\t%d\t%d\t%d\n", u, seq2user_[u], (int)v.size(), t);
+      for (size_t j = 0; j < w.size(); ++j) t += w[j];
+      fprintf(f, "%d\t%d\t%d\t%d\n", u, seq2user_[u], (int)w.size(), t);
     }
     fclose(f);
   }
   f = fopen((outdir + "/byitems.tsv").c_str(), "w");
   if (f) {
     for (uint32_t i = 0; i < m(); ++i) {
-      const std::vector<uint32_t> &v = item_users_[i];
-      if (v.empty()) continue;
-      uint32_t t = 0;
-      for (size_t j = 0; j < v.size(); ++j) t += r(v[j], i);
-      fprintf(f, "%d\t%d\t%d\t%d\n", i, seq2item_[i], (int)v.size(), t);
+      if (item_degree_[i] == 0) continue;
+      fprintf(f, "%d\t%d\t%d\t%d\n", i, seq2item_[i], (int)item_degree_[i], (uint32_t)item_total_[i]);
     }
     fclose(f);
   }

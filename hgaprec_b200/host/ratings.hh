@@ -10,6 +10,10 @@
 // are truncated to uint8 (yval_t, src/env.hh:20), ratings of class 0 are
 // dropped (src/ratings.hh:191-197), and held-out lines whose user or item was
 // never seen in training are dropped (src/ratings.cc:79-81).
+//
+// Unlike the reference (fscanf + a std::map node per rating, minutes and tens of
+// GB at Netflix scale) the reader parses the file from a large buffer and keeps
+// 5 bytes per rating: per user the item list and a parallel value list.
 #ifndef HPF_HOST_RATINGS_HH
 #define HPF_HOST_RATINGS_HH
 #include <stdint.h>
@@ -26,7 +30,27 @@ namespace hpfhost {
 typedef std::pair<uint32_t, uint32_t> Pair;          // (user seq, item seq): the reference's Rating
 typedef std::map<Pair, uint8_t> HeldoutMap;          // CountMap, iterated in (user, item) order
 
-struct Options;
+// whitespace-separated unsigned integers from a file, three per record ("%u\t%u\t%u\n")
+class TripleReader {
+public:
+  explicit TripleReader(FILE *f) : f_(f), buf_(1 << 22), pos_(0), end_(0) {}
+  bool next(uint32_t *a, uint32_t *b, uint32_t *c) { return number(a) && number(b) && number(c); }
+  bool number(uint32_t *out);
+
+private:
+  int get()
+  {
+    if (pos_ == end_) {
+      end_ = fread(buf_.data(), 1, buf_.size(), f_);
+      pos_ = 0;
+      if (end_ == 0) return -1;
+    }
+    return (unsigned char)buf_[pos_++];
+  }
+  FILE *f_;
+  std::vector<char> buf_;
+  size_t pos_, end_;
+};
 
 class Ratings {
 public:
@@ -40,20 +64,26 @@ public:
   // test_users.tsv -> set of user seqs (Ratings::read_test_users, src/ratings.cc:273-292)
   bool read_test_users(const std::string &path, std::map<uint32_t, bool> *out) const;
 
-  uint32_t n() const { return (uint32_t)user_items_.size(); }
-  uint32_t m() const { return (uint32_t)item_users_.size(); }
+  uint32_t n() const { return (uint32_t)items_.size(); }
+  uint32_t m() const { return (uint32_t)seq2item_.size(); }
   uint64_t nratings() const { return nratings_; }
   uint32_t user_id(uint32_t seq) const { return seq2user_[seq]; }
   uint32_t item_id(uint32_t seq) const { return seq2item_[seq]; }
   const std::vector<uint32_t> &seq2user() const { return seq2user_; }
   const std::vector<uint32_t> &seq2item() const { return seq2item_; }
-  const std::vector<uint32_t> &items_of(uint32_t u) const { return user_items_[u]; }
-  const std::vector<uint32_t> &users_of(uint32_t i) const { return item_users_[i]; }
+  // Ratings::get_movies(n): the user's items in file order (a repeated line appears twice)
+  const std::vector<uint32_t> &items_of(uint32_t u) const { return items_[u]; }
+  // value the reference's loops read for the j-th entry of user u: Ratings::r(u, items_of(u)[j])
+  uint32_t value_at(uint32_t u, size_t j) const { return vals_[u][j]; }
+  // Ratings::get_users(m)->size(): lines that named the item
+  uint32_t item_degree(uint32_t i) const { return item_degree_[i]; }
   // Ratings::r(n, m): 0 when absent (src/ratings.hh:153-165)
   uint32_t r(uint32_t u, uint32_t i) const
   {
-    std::unordered_map<uint64_t, uint8_t>::const_iterator it = value_.find(((uint64_t)u << 32) | i);
-    return it == value_.end() ? 0u : it->second;
+    const std::vector<uint32_t> &v = items_[u];
+    for (size_t j = 0; j < v.size(); ++j)
+      if (v[j] == i) return vals_[u][j];
+    return 0u;
   }
   bool test_hit(uint32_t v) const { return binary_ ? v >= 1 : v >= threshold_; }
 
@@ -66,14 +96,17 @@ public:
 
 private:
   uint32_t rating_class(uint32_t v) const { return binary_ ? (v >= threshold_ ? 1u : 0u) : v; }
+  void finalize(); // repeated (user, item) lines take the last value; per-item degree and rating total
   uint32_t max_users_, max_items_;
   bool binary_;
   uint32_t threshold_;
   uint64_t nratings_;
   std::unordered_map<uint32_t, uint32_t> user2seq_, item2seq_;
   std::vector<uint32_t> seq2user_, seq2item_;
-  std::vector<std::vector<uint32_t> > user_items_, item_users_;
-  std::unordered_map<uint64_t, uint8_t> value_;
+  std::vector<std::vector<uint32_t> > items_;
+  std::vector<std::vector<uint8_t> > vals_;
+  std::vector<uint32_t> item_degree_;
+  std::vector<uint64_t> item_total_;
 };
 
 } // namespace hpfhost
