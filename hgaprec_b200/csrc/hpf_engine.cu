@@ -849,7 +849,10 @@ int launch_dense_head(hpf_ctx *c)
   if (!d.on) return 0;
   const uint32_t n = c->th.R, n_pad = d.ntiles * head::kUsers;
   if (d.a_dirty) {
-    topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->K, nullptr, 0, nullptr, n, n_pad, head::kFact, d.a_hi, d.a_lo);
+    if (c->bias)
+      head::split_aux_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->Kp, c->th.aux, 0, nullptr, n, n_pad, d.a_hi, d.a_lo);
+    else
+      topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.A, c->ld, c->K, nullptr, 0, nullptr, n, n_pad, head::kFact, d.a_hi, d.a_lo);
     c->launches++;
     d.a_dirty = false;
   }
@@ -860,15 +863,20 @@ int launch_dense_head(hpf_ctx *c)
     const size_t boff = (size_t)b * head::kHead * head::kFact;
     const uint32_t *ids = d.head_ids + (size_t)b * head::kHead;
     float *part = d.dB_part + (size_t)b * grid * head::kHead * head::kFact;
-    topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, ids, nh, head::kHead, head::kFact, d.b_hi + boff, d.b_lo + boff);
+    if (c->bias)
+      head::split_aux_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->Kp, c->be.aux, 1, ids, nh, head::kHead, d.b_hi + boff, d.b_lo + boff);
+    else
+      topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, ids, nh, head::kHead, head::kFact, d.b_hi + boff, d.b_lo + boff);
     head::HeadArgs a;
     a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
     a.Y = reinterpret_cast<const uint8_t *>(d.Yw) + (size_t)b * n_pad * head::kHead; a.head_ids = ids;
     a.T_theta = c->th.T; a.dB_part = part;
     a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
     a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
+    a.Tb_theta = c->bias ? c->th.Tb : nullptr;
+    a.ElogbT = c->th.b_Elog; a.ElogbB = c->be.b_Elog; a.TbdirectT = c->th.Tbdirect; a.TbdirectB = c->be.Tbdirect;
     head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
-    head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T);
+    head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T, c->bias ? c->be.Tb : nullptr);
     c->launches += 3;
   }
   CU(cudaGetLastError());
@@ -1103,7 +1111,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   const uint64_t it_tiles = TR ? ((uint64_t)n + TR - 1) / TR : 0;
   const bool try_item_tile = c->item_tile_mode != 0 && TR > 0 && nnz > 0 && it_tiles * m < 0xfffffff0ull;
   const bool try_head_tile = c->head_tile_mode != 0 && TR > 0 && nnz > 0;
-  const bool try_dense = c->dense_head_mode != 0 && !c->bias && c->Kp <= (uint32_t)head::kFact && nnz > 0 && !try_item_tile;
+  const bool try_dense = c->dense_head_mode != 0 && c->Kp + (c->bias ? 2u : 0u) <= (uint32_t)head::kFact && nnz > 0 && !try_item_tile;
   const bool want_deg = try_head_tile || try_dense;
   c->dense.on = false;
   size_t cub_bytes = 0, scan_bytes = 0;
@@ -1238,6 +1246,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   uint64_t *h_tailptr = nullptr, *d_tailptr = nullptr, *d_headptr = nullptr;
   TileCount htc;
   uint64_t *h_counts = pin.get<uint64_t>(2); // {tail nnz, -}
+  uint32_t *h_yovf = nullptr;                // dense head: a cell of the byte matrix Y overflowed
   if (!h_counts) return fail(c, HPF_ENOMEM, "pinned arena too small");
   if (split_head) {
     TilePlan &hp = c->head_tile;
@@ -1282,7 +1291,12 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
       CU(cudaMemsetAsync(dp.Yw, 0, NB * n_pad * head::kHead, c->stream));
       CU(cudaMemsetAsync(dp.head_ids, 0xff, NB * head::kHead * 4, c->stream));
       CU(cudaMemcpyAsync(dp.head_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
-      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, n_pad * head::kHead, dp.Yw);
+      h_yovf = pin.get<uint32_t>(1);
+      if (!h_yovf) return fail(c, HPF_ENOMEM, "pinned arena too small");
+      *h_yovf = 0;
+      CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream)); // free again: stage 1 has read the index check
+      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, n_pad * head::kHead, dp.Yw, c->scratch_u32);
+      CU(cudaMemcpyAsync(h_yovf, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
       c->launches++;
       bool maps_ok = make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) &&
                      make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers);
@@ -1304,6 +1318,15 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   tr.mark("stage 2: work lists, split");
+  if (dense_head && h_yovf != nullptr && *h_yovf != 0) {
+    // repeated (user, head item) lines whose ratings add up past 255 do not fit a byte of Y (the reference walks every
+    // line, hgaprec.cc:1340-1366, so the sum is what counts): plan this input again without the dense head
+    const int mode = c->dense_head_mode;
+    c->dense_head_mode = 0;
+    const int rc = hpf_set_ratings_csr(c, row_ptr, col_idx, y);
+    c->dense_head_mode = mode;
+    return rc;
+  }
 
   // ================= stage 3: remaining host work lists, head work list, uploads =================
   if (!item_tile && try_item_tile) TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw, skip_ptr));
@@ -1405,6 +1428,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
     c->launches += 4;
     s.have_bias = true;
     c->aux_dirty = true;
+    if (theta_side) c->dense.a_dirty = true; // the operand copy of A carries the user-bias columns
     break;
   }
   default:

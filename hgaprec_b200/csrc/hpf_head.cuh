@@ -74,6 +74,11 @@ struct HeadArgs {
   const uint32_t *head_ids; // [128] item row of each head slot (0xffffffff: unused slot)
   float *T_theta;        // [n x ld]  += O        (rows owned by this tile: plain read-modify-write)
   float *dB_part;        // [gridDim.x x 128 x 128]  this CTA's dB, summed in a fixed order by head_reduce_kernel
+  // -bias: operand columns K, K+1 carry {aux.x, aux.y} (users) / {aux.y, aux.x} (items), so that Z gains the two
+  // bias slots of phi, O[:, K] is the user-bias sum and dB[:, K+1] the item-bias sum (hgaprec.cc:222-239, 1361-1364)
+  float *Tb_theta;       // [n] += O[:, K]   (nullptr without -bias)
+  const float *ElogbT, *ElogbB;
+  float *TbdirectT, *TbdirectB;
   // exact fallback for a pair whose Z left the fp32 range
   const float *ElogT, *ElogB;
   float *TdirectT, *TdirectB;
@@ -85,15 +90,21 @@ struct HeadArgs {
 __device__ __noinline__ void slow_pair(const HeadArgs &a, uint32_t u, uint32_t it, float yv)
 {
   const float *et = a.ElogT + (size_t)u * a.ld, *eb = a.ElogB + (size_t)it * a.ld;
-  float mx = -CUDART_INF_F;
-  for (uint32_t k = 0; k < a.K; ++k) mx = fmaxf(mx, et[k] + eb[k]);
-  float sum = 0.f;
+  const bool bias = a.Tb_theta != nullptr;
+  const float xbu = bias ? a.ElogbT[u] : -CUDART_INF_F, xbi = bias ? a.ElogbB[it] : -CUDART_INF_F;
+  float mx = fmaxf(xbu, xbi);
+  for (uint32_t k = 0; k < a.K; ++k) mx = fmaxf(mx, et[k] + eb[k]); // pad columns hold -inf
+  float sum = bias ? expf(xbu - mx) + expf(xbi - mx) : 0.f;
   for (uint32_t k = 0; k < a.K; ++k) sum += expf(et[k] + eb[k] - mx);
   const float sc = yv / sum;
   for (uint32_t k = 0; k < a.K; ++k) {
     const float v = sc * expf(et[k] + eb[k] - mx);
     atomicAdd(a.TdirectT + (size_t)u * a.ld + k, v);
     atomicAdd(a.TdirectB + (size_t)it * a.ld + k, v);
+  }
+  if (bias) {
+    atomicAdd(a.TbdirectT + u, sc * expf(xbu - mx));
+    atomicAdd(a.TbdirectB + it, sc * expf(xbi - mx));
   }
   atomicAdd(a.slow_count, 2ull); // the gather path counts a nonzero once per pass
   *a.flagT = 1u;
@@ -256,10 +267,11 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         uint32_t o[32];
         tc_ld32(tm_o + lane_addr + c * 32u, o);
         tc_wait_ld();
-        if (u < a.n && c * 32u < a.K) {
+        if (u < a.n && c * 32u <= a.K) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const uint32_t k = c * 32u + j;
+            if (k == a.K && a.Tb_theta != nullptr) a.Tb_theta[u] += __uint_as_float(o[j]); // the user-bias slot of phi
             if (k < a.K) { // K is a multiple of 4 in storage (Kp): whole float4s, pad lanes are zero on both sides
               float4 t = *reinterpret_cast<float4 *>(trow + k);
               t.x += __uint_as_float(o[j]); t.y += __uint_as_float(o[j + 1]);
@@ -305,8 +317,10 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 // dense ratings of the head block: Y[u * 128 + slot] += y for every nonzero of a head item
 // (a repeated (user, item) line adds up: same Z, so the contributions add as in the reference's walk)
 // slot s = block * 128 + position; every block has its own [n_pad x 128] byte matrix (block_stride bytes apart)
+// A cell is one byte: repeated lines whose ratings add up past 255 do not fit.  The add that crosses 255 sees it in
+// the value atomicAdd returns and raises *overflow; hpf_set_ratings_csr then plans without the dense head.
 __global__ void dense_y_kernel(const uint32_t *row_of, const uint32_t *col, const uint8_t *y, const uint32_t *slot_of, uint64_t nnz,
-                               size_t block_stride, uint32_t *Yw)
+                               size_t block_stride, uint32_t *Yw, uint32_t *overflow)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
@@ -314,14 +328,43 @@ __global__ void dense_y_kernel(const uint32_t *row_of, const uint32_t *col, cons
   if (s == 0xffffffffu) return;
   const uint32_t yv = y ? y[j] : 1u;
   const size_t e = (size_t)(s / kHead) * block_stride + (size_t)row_of[j] * kHead + (s % kHead);
-  atomicAdd(Yw + (e >> 2), yv << ((e & 3u) * 8u));
+  const uint32_t sh = (uint32_t)(e & 3u) * 8u;
+  const uint32_t old = atomicAdd(Yw + (e >> 2), yv << sh);
+  if (((old >> sh) & 0xffu) + yv > 255u) *overflow = 1u;
+}
+
+// split-bf16 operand rows with the two -bias columns: [A_r (K values) | 0.. | at Kp: aux.x, aux.y (users) or aux.y, aux.x (items)]
+__global__ void __launch_bounds__(256) split_aux_kernel(const float *A, uint32_t ld, uint32_t Kp, const float2 *aux, int swap,
+                                                        const uint32_t *gather, uint32_t rows, uint32_t rows_pad,
+                                                        __nv_bfloat16 *hi, __nv_bfloat16 *lo)
+{
+  const uint64_t total = (uint64_t)rows_pad * kFact;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(e / kFact), k = (uint32_t)(e % kFact);
+    float v = 0.f;
+    if (r < rows) {
+      const uint32_t src = gather ? gather[r] : r;
+      if (k < Kp) v = A[(size_t)src * ld + k];
+      else if (k == Kp) v = swap ? aux[src].y : aux[src].x;
+      else if (k == Kp + 1) v = swap ? aux[src].x : aux[src].y;
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
 }
 
 // T_beta[head item] = sum over CTAs of their dB partials, in CTA order (deterministic); pad columns 0
-__global__ void head_reduce_kernel(const float *dB_part, uint32_t nparts, const uint32_t *head_ids, uint32_t Kp, uint32_t ld, float *T)
+__global__ void head_reduce_kernel(const float *dB_part, uint32_t nparts, const uint32_t *head_ids, uint32_t Kp, uint32_t ld, float *T,
+                                   float *Tb)
 {
   const uint32_t it = head_ids[blockIdx.x];
   if (it == 0xffffffffu) return;
+  if (Tb != nullptr && threadIdx.x == 0) { // -bias: column Kp + 1 of dB is the item-bias sum
+    float s = 0.f;
+    for (uint32_t p = 0; p < nparts; ++p) s += dB_part[((size_t)p * kHead + blockIdx.x) * kFact + Kp + 1];
+    Tb[it] = s;
+  }
   for (uint32_t k = threadIdx.x; k < ld; k += blockDim.x) {
     float s = 0.f;
     if (k < Kp)

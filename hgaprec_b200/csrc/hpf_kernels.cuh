@@ -756,7 +756,15 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
         a.b_rate[r] = br;
         a.b_Ev[r] = sa / rb;
         a.b_Elog[r] = bel;
-        a.aux[r] = make_float2(expf(bel - mx), expf(-mx));
+        const float2 ax = make_float2(expf(bel - mx), expf(-mx));
+        a.aux[r] = ax;
+        if (a.split_hi != nullptr) { // the two bias columns of the dense head's operand copy
+          const size_t o = (size_t)r * a.split_ld + a.Kp;
+          const __nv_bfloat16 hx = __float2bfloat16_rn(ax.x), hy = __float2bfloat16_rn(ax.y);
+          a.split_hi[o] = hx; a.split_hi[o + 1] = hy;
+          a.split_lo[o] = __float2bfloat16_rn(ax.x - __bfloat162float(hx));
+          a.split_lo[o + 1] = __float2bfloat16_rn(ax.y - __bfloat162float(hy));
+        }
       }
     }
   }

@@ -157,6 +157,9 @@ def test_l2_tiled_orderings_match_oracle(monkeypatch, flags, tile_kb):
     ("bpf K=33 fewer items than head slots", 700, 90, 20000, 33, 0, False),
     ("hier binary K=128", 1000, 400, 60000, 128, H.HIER | H.BINARY, True),
     ("bpf jacobi-less K=5, users not a multiple of 128", 517, 300, 15000, 5, 0, False),
+    ("hier bias K=100", 3000, 1500, 200000, 100, H.HIER | H.BIAS, False),
+    ("bpf bias -novb K=64 (bias columns open a new 32-column chunk)", 900, 500, 40000, 64, H.BIAS | H.JACOBI, False),
+    ("bpf bias K=124: Kp + 2 = 126 operand columns, the widest that fits", 600, 300, 20000, 124, H.BIAS, False),
 ])
 def test_dense_head_matches_oracle_and_gather_plan(monkeypatch, dense, name, n, m, nnz, k, flags, binary):
     """The tcgen05 dense head (forced on / off) against the oracle: three iterations, duplicates included."""
@@ -170,6 +173,27 @@ def test_dense_head_matches_oracle_and_gather_plan(monkeypatch, dense, name, n, 
     assert (st["head_nnz"] > 0) == (dense == "1") and st["slow_path_nnz"] == 0
     bad = util.compare_states(got, want, rel=6e-5, elog_abs=6e-5)
     assert not bad, (name, bad)
+
+
+@pytest.mark.parametrize("flags", [H.HIER, H.HIER | H.BIAS])
+def test_dense_head_cell_overflow_plans_without_the_head(monkeypatch, flags):
+    """The dense ratings block keeps one byte per (user, head item).  Repeated lines for one pair add up (the
+    reference walks every line, hgaprec.cc:1340-1366); a sum past 255 does not fit, the set-up has to notice and
+    plan without the dense head.  A sum of exactly 255 still fits."""
+    monkeypatch.setenv("HPF_DENSE_HEAD", "1")
+    monkeypatch.setenv("HPF_DENSE_BLOCK_SHARE", "0")  # m = 300: every item is a head item
+    d, s = _oracle_case(900, 300, 40000, 32, flags, seed=71)
+    rp, ci, y = d["row_ptr"].astype(np.int64), d["col_idx"].copy(), d["y"].copy()
+    u = int(np.argmax(np.diff(rp) >= 3))
+    b = int(rp[u])
+    ci[b + 1] = ci[b + 2] = ci[b]  # three lines for one (user, item) pair
+    for last, head_on in ((6, False), (5, True)):
+        y[b], y[b + 1], y[b + 2] = 200, 50, last
+        want = s.copy().iterate(rp, ci, y, 2, nthreads=8)
+        got, st = run_engine(s, rp, ci, y, 2)
+        assert (st["head_nnz"] > 0) == head_on
+        bad = util.compare_states(got, want, rel=6e-5, elog_abs=6e-5)
+        assert not bad, (last, bad)
 
 
 def test_no_ratings_at_all_and_y_null():
@@ -212,9 +236,9 @@ def test_exact_fallback_when_products_underflow():
     assert not util.compare_states(got2, want, rel=6e-5, elog_abs=6e-5)
 
 
-@pytest.mark.parametrize("flags,dense", [(H.HIER | H.BIAS, False), (H.HIER, True), (0, True)])
+@pytest.mark.parametrize("flags,dense", [(H.HIER | H.BIAS, True), (H.HIER, True), (0, True)])
 def test_default_plan_is_bitwise_deterministic(flags, dense):
-    """The default plan (gather kernel for the tail, dense tcgen05 head where it applies: no bias, K <= 128)
+    """The default plan (gather kernel for the tail, dense tcgen05 head where it applies: K (+2 with bias) <= 128)
     sums in a fixed order."""
     d, s = _oracle_case(2000, 700, 90000, 100, flags, seed=8)
     a, st = run_engine(s, d["row_ptr"], d["col_idx"], d["y"], 3)
