@@ -5,6 +5,7 @@
 #include "hpf_oracle.h"
 #include "gsl_shim/gsl/gsl_rng.h"    /* own mt19937 (same stream the _ref build uses) */
 #include "gsl_shim/gsl/gsl_sf_psi.h" /* own digamma  (same one the _ref build uses)  */
+#include "gsl_shim/gsl/gsl_sf.h"     /* gsl_sf_lngamma stand-in (same one the _ref build uses) */
 
 #include <math.h>
 #include <stdlib.h>
@@ -400,4 +401,108 @@ void hpf_oracle_topn(const hpf_oracle_state *s, const uint32_t *users, uint32_t 
     }
   }
   free(lst);
+}
+
+/* ------------------------------------------------------------------ ELBO */
+
+/* GPMatrix::compute_elbo_term_helper (src/gpbase.hh:360-387) for a rows x k set whose rate is a
+ * matrix (rate_is_vector == 0: GPMatrix) or a k-vector (GPMatrixGR::compute_elbo_term_helper,
+ * 717-741).  row_prior / row_log_prior: _hier_rprior / _hier_log_rprior (only a GPMatrix after
+ * set_prior_rate, i.e. htheta / hbeta); NULL selects the constant (_sprior, _rprior) branch. */
+static double elbo_matrix(double *const g[4], uint32_t rows, uint32_t k, int rate_is_vector,
+                          const double *row_prior, const double *row_log_prior)
+{
+  double s = 0.0;
+  for (uint32_t n = 0; n < rows; ++n) {
+    const double *ev = g[HPF_O_EV] + (size_t)n * k, *el = g[HPF_O_ELOGV] + (size_t)n * k;
+    for (uint32_t q = 0; q < k; ++q) {
+      if (row_prior) {
+        s += PRIOR_SHAPE * row_log_prior[n] + (PRIOR_SHAPE - 1) * el[q];
+        s -= row_prior[n] * ev[q] + gsl_sf_lngamma(PRIOR_SHAPE);
+      } else {
+        s += PRIOR_SHAPE * log(PRIOR_RATE) + (PRIOR_SHAPE - 1) * el[q];
+        s -= PRIOR_RATE * ev[q] + gsl_sf_lngamma(PRIOR_SHAPE);
+      }
+    }
+    for (uint32_t q = 0; q < k; ++q) {
+      const double a = floor30(g[HPF_O_SHAPE][(size_t)n * k + q]);
+      const double b = floor30(rate_is_vector ? g[HPF_O_RATE][q] : g[HPF_O_RATE][(size_t)n * k + q]);
+      s -= a * log(b) + (a - 1) * el[q];
+      s += b * ev[q] + gsl_sf_lngamma(a);
+    }
+  }
+  return s;
+}
+
+/* GPArray::compute_elbo_term_helper, src/gpbase.hh:951-969 */
+static double elbo_array(double *const g[4], uint32_t rows)
+{
+  double s = 0.0;
+  for (uint32_t n = 0; n < rows; ++n) {
+    const double a = floor30(g[HPF_O_SHAPE][n]), b = floor30(g[HPF_O_RATE][n]);
+    const double ev = g[HPF_O_EV][n], el = g[HPF_O_ELOGV][n];
+    s += PRIOR_SHAPE * log(PRIOR_RATE) + (PRIOR_SHAPE - 1) * el;
+    s -= PRIOR_RATE * ev + gsl_sf_lngamma(PRIOR_SHAPE);
+    s -= a * log(b) + (a - 1) * el;
+    s += b * ev + gsl_sf_lngamma(a);
+  }
+  return s;
+}
+
+/* HGAPRec::logl, src/hgaprec.cc:2160-2255, as coded: phi is scaled by y BEFORE the entropy-like
+ * term (2214-2220), so a rating y > 1 enters as y * (y phi_k) * (Elog - log(y phi_k)). */
+double hpf_oracle_elbo(const hpf_oracle_state *s, const uint64_t *row_ptr, const uint32_t *col_idx,
+                       const uint8_t *y, const double *xi_ev, const double *xi_elog,
+                       const double *eta_ev, const double *eta_elog)
+{
+  const uint32_t n = s->n, m = s->m, k = s->k;
+  const int hier = (s->flags & HPF_O_HIER) != 0;
+  const int bias = (s->flags & HPF_O_BIAS) != 0;
+  const uint32_t width = bias ? k + 2 : k;
+  double *phi = malloc(sizeof(double) * (k + 2));
+  double tot = 0.0;
+  for (uint32_t u = 0; u < n; ++u) {
+    for (uint64_t j = row_ptr[u]; j < row_ptr[u + 1]; ++j) {
+      const uint32_t i = col_idx[j];
+      const double yv = y ? (double)y[j] : 1.0;
+      const double *tl = s->theta[HPF_O_ELOGV] + (size_t)u * k, *bl = s->beta[HPF_O_ELOGV] + (size_t)i * k;
+      const double *te = s->theta[HPF_O_EV] + (size_t)u * k, *be = s->beta[HPF_O_EV] + (size_t)i * k;
+      for (uint32_t q = 0; q < k; ++q) phi[q] = tl[q] + bl[q];
+      if (bias) {
+        phi[k] = s->thetabias[HPF_O_ELOGV][u];
+        phi[k + 1] = s->betabias[HPF_O_ELOGV][i];
+      }
+      const double lz = logsum_stream(phi, width);
+      for (uint32_t q = 0; q < width; ++q) phi[q] = exp(phi[q] - lz);
+      if (yv > 1)
+        for (uint32_t q = 0; q < width; ++q) phi[q] *= yv;
+      double v = 0.0;
+      for (uint32_t q = 0; q < k; ++q) v += yv * phi[q] * (tl[q] + bl[q] - log(phi[q]));
+      tot += v;
+      if (bias) {
+        tot += yv * phi[k] * (s->thetabias[HPF_O_ELOGV][u] - log(phi[k]));
+        tot += yv * phi[k + 1] * (s->betabias[HPF_O_ELOGV][i] - log(phi[k + 1]));
+      }
+      for (uint32_t q = 0; q < k; ++q) tot -= te[q] * be[q];
+      if (bias) {
+        tot -= s->thetabias[HPF_O_EV][u];
+        tot -= s->betabias[HPF_O_EV][i];
+      }
+    }
+  }
+  free(phi);
+  if (!hier) {
+    tot += elbo_matrix(s->theta, n, k, 1, NULL, NULL);
+    tot += elbo_matrix(s->beta, m, k, 1, NULL, NULL);
+  } else {
+    tot += elbo_matrix(s->theta, n, k, 0, xi_ev, xi_elog);
+    tot += elbo_matrix(s->beta, m, k, 0, eta_ev, eta_elog);
+    tot += elbo_array(s->thetarate, n);
+    tot += elbo_array(s->betarate, m);
+  }
+  if (bias) { /* n x 1 / m x 1 GPMatrix that never saw set_prior_rate: constant-prior branch */
+    tot += elbo_matrix(s->thetabias, n, 1, 0, NULL, NULL);
+    tot += elbo_matrix(s->betabias, m, 1, 0, NULL, NULL);
+  }
+  return tot;
 }

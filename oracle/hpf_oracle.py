@@ -58,6 +58,8 @@ def lib():
         L.hpf_oracle_heldout.restype = ctypes.c_double
         L.hpf_oracle_heldout.argtypes = [ctypes.POINTER(_CState), ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_uint64]
+        L.hpf_oracle_elbo.restype = ctypes.c_double
+        L.hpf_oracle_elbo.argtypes = [ctypes.POINTER(_CState)] + [ctypes.c_void_p] * 7
         L.hpf_oracle_topn.argtypes = [ctypes.POINTER(_CState), ctypes.c_void_p, ctypes.c_uint32,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
                                       ctypes.c_void_p, ctypes.c_void_p]
@@ -122,9 +124,30 @@ class OracleState:
         col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
         yy = None if y is None else np.ascontiguousarray(y, dtype=np.uint8)
         c = self._c()
-        lib().hpf_oracle_iterate(ctypes.byref(c), _ptr(row_ptr), _ptr(col_idx),
-                                 None if yy is None else _ptr(yy), int(niters), int(nthreads))
+        # the last iteration runs on its own so that the rate priors it saw (set_prior_rate, gpbase.hh:163-173:
+        # E[xi], E[log xi], E[eta], E[log eta] BEFORE that iteration's xi / eta update) can be kept for elbo()
+        for part in (int(niters) - 1, 1) if niters >= 1 else ():
+            if part == 1:
+                self.rate_prior = tuple(self.p[g][f].copy() for g in ("thetarate", "betarate") for f in ("Ev", "Elogv"))
+            if part > 0:
+                lib().hpf_oracle_iterate(ctypes.byref(c), _ptr(row_ptr), _ptr(col_idx),
+                                         None if yy is None else _ptr(yy), part, int(nthreads))
         return self
+
+    def elbo(self, row_ptr, col_idx, y, rate_prior=None):
+        """HGAPRec::logl (hgaprec.cc:2160-2255).  rate_prior = (E[xi], E[log xi], E[eta], E[log eta]) as the last
+        iteration's set_prior_rate saw them; default: what the last iterate() call kept (hier only)."""
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        yy = None if y is None else np.ascontiguousarray(y, dtype=np.uint8)
+        pri = [None] * 4
+        if self.hier:
+            rp = rate_prior if rate_prior is not None else getattr(self, "rate_prior", None)
+            assert rp is not None, "hier ELBO needs the rate priors of the last iteration (iterate() first)"
+            pri = [np.ascontiguousarray(a, dtype=np.float64) for a in rp]
+        c = self._c()
+        return lib().hpf_oracle_elbo(ctypes.byref(c), _ptr(row_ptr), _ptr(col_idx), None if yy is None else _ptr(yy),
+                                     *[None if a is None else _ptr(a) for a in pri])
 
     def heldout(self, u, i, y):
         u = np.ascontiguousarray(u, dtype=np.uint32)

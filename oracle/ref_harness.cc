@@ -136,7 +136,6 @@ static void dump_state(uint32_t T)
                      (double)g_env->binary_data, (double)g_env->vb };
   uint64_t md[1] = { 8 };
   rec(f, "meta", 0, 1, md, meta, 8);
-  (void)one;
 
   // training matrix exactly as the hot loop walks it: get_movies(n) order,
   // value through Ratings::r(n,m) (hgaprec.cc:1342-1345).
@@ -191,6 +190,25 @@ static void dump_state(uint32_t T)
   }
   rec_heldout(f, "validation", h._validation_map, g_env->hier);
   rec_heldout(f, "test", h._test_map, g_env->hier);
+  if (T > 0) {
+    // the reference's own HGAPRec::logl() (hgaprec.cc:2160-2255) on this state: it appends "%.5f\n" to logl.txt
+    // (_af, hgaprec.cc:56); read that line back.  With -hier the Gamma terms use the rate priors the last
+    // set_prior_rate stored (gpbase.hh:163-173, 369-373): dump those too.
+    fflush(h._af);
+    long off = ftell(h._af);
+    h.logl();
+    double elbo = 0;
+    FILE *lf = fopen(Env::file_str("/logl.txt").c_str(), "r");
+    if (!lf || fseek(lf, off, SEEK_SET) != 0 || fscanf(lf, "%lf", &elbo) != 1) { perror("logl.txt"); _exit(4); }
+    fclose(lf);
+    rec(f, "elbo", 0, 1, one, &elbo, 8);
+    if (g_env->hier) {
+      rec_array(f, "htheta.hier_rprior", h._htheta._hier_rprior);
+      rec_array(f, "htheta.hier_log_rprior", h._htheta._hier_log_rprior);
+      rec_array(f, "hbeta.hier_rprior", h._hbeta._hier_rprior);
+      rec_array(f, "hbeta.hier_log_rprior", h._hbeta._hier_log_rprior);
+    }
+  }
   fclose(f);
   fprintf(stderr, "[ref_harness] wrote %s\n", path);
 }

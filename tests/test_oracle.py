@@ -41,6 +41,25 @@ def test_oracle_matches_reference_golden(mode):
             assert abs(ll - ref) <= 1e-9 * max(1.0, abs(ref)), (mode, split, t)
 
 
+@pytest.mark.parametrize("mode", util.MODES)
+@pytest.mark.parametrize("t", (1, 3))
+def test_oracle_elbo_matches_reference_logl(mode, t):
+    """hpf_oracle_elbo against the value the reference's own HGAPRec::logl() wrote to logl.txt on the same state
+    (oracle/ref_harness.cc calls it; "%.5f"), both from the reference's state and from the oracle's own iterations."""
+    g = util.load_golden(mode)
+    rp, ci, y = g["csr.row_ptr"], g["csr.col_idx"], g["csr.y"]
+    ref = float(g["T%d/elbo" % t][0])
+    on_ref_state = util.golden_state(g, t).elbo(rp, ci, y, rate_prior=util.golden_rate_prior(g, t))
+    assert abs(on_ref_state - ref) <= util.TOL_ELBO_REF_PRINT
+    iterated = util.golden_state(g, 0).iterate(rp, ci, y, t)
+    assert abs(iterated.elbo(rp, ci, y) - ref) <= util.TOL_ELBO_REF_PRINT
+    # one call of t iterations and t calls of one iteration keep the same rate priors
+    step = util.golden_state(g, 0)
+    for _ in range(t):
+        step.iterate(rp, ci, y, 1)
+    assert step.elbo(rp, ci, y) == iterated.elbo(rp, ci, y)
+
+
 @pytest.mark.parametrize("mode", ("hier", "bpf_bias"))
 def test_oracle_init_matches_reference_golden(mode):
     g = util.load_golden(mode)

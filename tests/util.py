@@ -29,6 +29,16 @@ def golden_state(g, t):
     return O.state_from_dump(d)
 
 
+def golden_rate_prior(g, t):
+    """The rate priors HGAPRec::logl() saw after t iterations of a -hier golden run (_hier_rprior, _hier_log_rprior
+    of htheta and hbeta, gpbase.hh:163-173), or None for the non-hier modes."""
+    keys = ["T%d/%s" % (t, k) for k in ("htheta.hier_rprior", "htheta.hier_log_rprior", "hbeta.hier_rprior", "hbeta.hier_log_rprior")]
+    return tuple(g[k] for k in keys) if keys[0] in g else None
+
+
+TOL_ELBO_REF_PRINT = 6e-6  # the reference prints logl with "%.5f" (hgaprec.cc:2253)
+
+
 def groups(state):
     gs = ["theta", "beta"]
     if state.hier:
