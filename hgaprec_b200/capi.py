@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("HPF_LIB") or os.path.join(HERE, "libhpf_b200.so")  # 
 CSRC = os.path.join(HERE, "csrc")
 
 ABI_VERSION = 1
-HIER, BIAS, BINARY, JACOBI = 1, 2, 4, 8
+HIER, BIAS, BINARY, JACOBI, LOGL = 1, 2, 4, 8, 16
 THETA, BETA, THETARATE, BETARATE, THETABIAS, BETABIAS = range(6)
 COMM_ID_BYTES = 128
 
@@ -83,6 +83,7 @@ def load_library():
     L.hpf_get_state.argtypes = [vp, cint, vp, vp, vp, vp]
     L.hpf_iterate.argtypes = [vp, u32]
     L.hpf_heldout_loglik.argtypes = [vp, vp, vp, vp, u64, ctypes.POINTER(ctypes.c_double)]
+    L.hpf_elbo.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.hpf_topn.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp]
     L.hpf_item_ranks.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp]
     L.hpf_partition_users.argtypes = [vp, u32, u32, vp]
@@ -216,6 +217,12 @@ class Engine:
         y = np.ascontiguousarray(y, dtype=np.uint8)
         out = ctypes.c_double(0.0)
         self._check(self._L.hpf_heldout_loglik(self._ctx, _p(u), _p(i), _p(y), len(u), ctypes.byref(out)))
+        return out.value
+
+    def elbo(self):
+        """HGAPRec::logl() (hgaprec.cc:2160-2255); the engine must have been created with the LOGL flag."""
+        out = ctypes.c_double(0.0)
+        self._check(self._L.hpf_elbo(self._ctx, ctypes.byref(out)))
         return out.value
 
     def topn(self, users, excl_ptr, excl_idx, topn):

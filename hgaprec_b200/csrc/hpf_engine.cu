@@ -21,6 +21,7 @@
 #include "hpf_kernels.cuh"
 #include "hpf_topn.cuh"
 #include "hpf_head.cuh"
+#include "hpf_elbo.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -133,6 +134,7 @@ struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
   CUtensorMap map_a_hi, map_a_lo, map_b_hi[4], map_b_lo[4];
 };
 constexpr uint32_t kMaxHeadBlocks = 4;
+constexpr uint32_t kElboLaunches = 7; // nnz, theta, beta, xi, eta, theta bias, beta bias
 
 struct WorkList {       // segments of one orientation, sorted by descending length
   uint4 *seg = nullptr;
@@ -149,6 +151,7 @@ struct Side {
   float *A = nullptr, *Elog = nullptr, *Ev = nullptr, *shape = nullptr, *rate = nullptr;
   float *T = nullptr, *Tpart = nullptr, *Tdirect = nullptr, *shift = nullptr;
   float *pr_shape = nullptr, *pr_rate = nullptr, *pr_Ev = nullptr;           // GPArray (hier)
+  float *pr_shape_prev = nullptr, *pr_rate_prev = nullptr; // HPF_LOGL: the GPArray as the last iteration's set_prior_rate saw it
   float *b_shape = nullptr, *b_rate = nullptr, *b_Ev = nullptr, *b_Elog = nullptr; // bias GPMatrix
   float *Tb = nullptr, *Tbpart = nullptr, *Tbdirect = nullptr;
   float2 *aux = nullptr;
@@ -204,6 +207,10 @@ struct hpf_ctx {
   float *colsum_theta_old = nullptr; // -novb
   unsigned long long *slow_count = nullptr;
   double *logfact = nullptr, *ll_blocks = nullptr, *ll_out = nullptr;
+  // HPF_LOGL (-logl): what hpf_elbo needs beyond the hot path's own state
+  bool logl = false, pr_prev_valid = false, csr_has_y = false;
+  uint64_t *csr_rowptr = nullptr; size_t csr_rowptr_cap = 0; // device copy of the CSR row pointer
+  double *elbo_blocks = nullptr;                             // [kElboLaunches x sm_count x 8] per-block partial sums
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -303,6 +310,10 @@ int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
     TRY(dalloc(c, &s.pr_shape, R));
     TRY(dalloc(c, &s.pr_rate, R));
     TRY(dalloc(c, &s.pr_Ev, R));
+    if (c->logl) {
+      TRY(dalloc(c, &s.pr_shape_prev, R));
+      TRY(dalloc(c, &s.pr_rate_prev, R));
+    }
   }
   if (c->bias) {
     TRY(dalloc(c, &s.b_shape, R));
@@ -900,6 +911,13 @@ int ensure_aux(hpf_ctx *c)
 
 int one_iteration(hpf_ctx *c)
 {
+  if (c->logl && c->hier) { // logl() sees the rate priors of THIS iteration's set_prior_rate (gpbase.hh:163-173)
+    CU(cudaMemcpyAsync(c->th.pr_shape_prev, c->th.pr_shape, sizeof(float) * c->th.R, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->th.pr_rate_prev, c->th.pr_rate, sizeof(float) * c->th.R, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->be.pr_shape_prev, c->be.pr_shape, sizeof(float) * c->be.R, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->be.pr_rate_prev, c->be.pr_rate, sizeof(float) * c->be.R, cudaMemcpyDeviceToDevice, c->stream));
+    c->pr_prev_valid = true;
+  }
   MARK(0);
   TRY(launch_sweep(c, c->th, c->be)); // user pass (CSR; the tail items when the head runs as a tile sweep): T_theta
   MARK(1);
@@ -1003,6 +1021,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   else for (n->ld = 4; n->ld < n->Kp; n->ld *= 2) {}
   n->hier = cfg->flags & HPF_HIER; n->bias = cfg->flags & HPF_BIAS; n->binary = cfg->flags & HPF_BINARY;
   n->jacobi = (cfg->flags & HPF_JACOBI) && !n->hier;
+  n->logl = cfg->flags & HPF_LOGL;
   cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   if (const char *e = getenv("HPF_SEG_LEN")) { int v = atoi(e); if (v >= 8 && v <= 65536) n->seg_len = v; }
   if (const char *e = getenv("HPF_L2_TILE_MB")) { int v = atoi(e); if (v >= 0 && v <= 4096) n->l2_tile_bytes = (uint64_t)v << 20; }
@@ -1057,6 +1076,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     if ((rc = dalloc(c, &c->logfact, 256))) break;
     if ((rc = dalloc(c, &c->ll_blocks, (size_t)c->sm_count * 8))) break;
     if ((rc = dalloc(c, &c->ll_out, 1))) break;
+    if (c->logl && (rc = dalloc(c, &c->elbo_blocks, (size_t)kElboLaunches * c->sm_count * 8))) break;
     double lf[256];
     lf[0] = lf[1] = log(1.0);
     for (int v = 2; v < 256; ++v) lf[v] = lf[v - 1] + log((double)v); // log_factorial, hgaprec.cc:1563-1570
@@ -1132,6 +1152,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   TRY(ensure(c, &c->csr_idx, &c->csr_idx_cap, nnz));
   if (y) TRY(ensure(c, &c->csr_y, &c->csr_y_cap, nnz));
   const uint8_t *d_y = y ? c->csr_y : nullptr;
+  c->csr_has_y = y != nullptr;
   Arena &dev = c->dev_arena, &pin = c->pin_arena;
   tr.mark("reserve");
 
@@ -1147,6 +1168,10 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (c->logl) { // hpf_elbo walks the ratings user by user
+      TRY(ensure(c, &c->csr_rowptr, &c->csr_rowptr_cap, (size_t)n + 1));
+      CU(cudaMemcpyAsync(c->csr_rowptr, d_rowptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
     check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32); // every item index must be < n_items
     expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
     c->launches += 2;
@@ -1412,6 +1437,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
     import_vector_kernel<<<nb, 256, 0, c->stream>>>(d2, R, s.pr_Ev);
     c->launches += 3;
     s.have_pr = true;
+    c->pr_prev_valid = false; // no iteration has used this xi / eta as a rate prior yet
     break;
   }
   case HPF_THETABIAS:
@@ -1591,6 +1617,78 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   }
   if (e != cudaSuccess) return fail(c, HPF_ECUDA, "hpf_heldout_loglik: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// HGAPRec::logl(), hgaprec.cc:2160-2255 (kernels and the algebra: hpf_elbo.cuh)
+int hpf_elbo(hpf_ctx *c, double *elbo_out)
+{
+  if (!c || !elbo_out) return fail(c, HPF_EINVAL, "null argument");
+  *elbo_out = 0.0;
+  if (!c->logl) return fail(c, HPF_EINVAL, "hpf_elbo needs a ctx created with HPF_LOGL");
+  TRY(check_ready(c));
+  if (c->hier && !c->pr_prev_valid)
+    return fail(c, HPF_EINVAL, "hpf_elbo with HPF_HIER needs at least one hpf_iterate since THETARATE/BETARATE were set "
+                               "(logl() uses the rate priors of the last iteration, gpbase.hh:163-173)");
+  CU(cudaSetDevice(c->cfg.device));
+  const uint32_t per = (uint32_t)c->sm_count * 8u; // partial sums per launch
+  CU(cudaMemsetAsync(c->elbo_blocks, 0, sizeof(double) * kElboLaunches * per, c->stream));
+  uint32_t slot = 0;
+  auto grid_for = [&](uint64_t threads) { return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(per, (threads + elbo::kThreads - 1) / elbo::kThreads)); };
+  // the nonzero terms of this ctx's users
+  if (c->nnz > 0) {
+    elbo::NnzArgs a;
+    a.row_ptr = c->csr_rowptr; a.idx = c->csr_idx; a.y = c->csr_has_y ? c->csr_y : nullptr;
+    a.n = c->th.R; a.K = c->K; a.ld = c->ld;
+    a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.EvT = c->th.Ev; a.EvB = c->be.Ev;
+    a.ElogbT = c->bias ? c->th.b_Elog : nullptr; a.ElogbB = c->bias ? c->be.b_Elog : nullptr;
+    a.EvbT = c->bias ? c->th.b_Ev : nullptr; a.EvbB = c->bias ? c->be.b_Ev : nullptr;
+    a.block_sums = c->elbo_blocks + (size_t)slot * per;
+    elbo::nnz_kernel<<<grid_for((uint64_t)c->th.R * 32), elbo::kThreads, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  ++slot;
+  // Gamma terms: the user side always, the item side on rank 0 only (it is replicated), so that the sum of
+  // hpf_elbo over the ranks is the ELBO of the whole problem
+  for (int side = 0; side < 2; ++side) {
+    Side &s = side == 0 ? c->th : c->be;
+    const bool mine = side == 0 || c->rank == 0;
+    if (mine && s.R > 0) {
+      elbo::GammaArgs g;
+      g.R = s.R; g.K = c->K; g.ld = c->ld;
+      g.shape = s.shape; g.rate = s.rate; g.Ev = s.Ev; g.Elog = s.Elog;
+      g.rate_is_vector = c->hier ? 0 : 1;
+      g.sprior = s.prior_shape; g.rprior = s.prior_rate; g.lg_sprior = lgamma(s.prior_shape);
+      g.pri_shape = c->hier ? s.pr_shape_prev : nullptr; g.pri_rate = c->hier ? s.pr_rate_prev : nullptr;
+      g.block_sums = c->elbo_blocks + (size_t)(slot + side) * per;
+      elbo::gamma_matrix_kernel<<<grid_for((uint64_t)s.R * c->K), elbo::kThreads, 0, c->stream>>>(g);
+      c->launches++;
+      if (c->hier) { // xi / eta (GPArray)
+        elbo::gamma_array_kernel<<<grid_for(s.R), elbo::kThreads, 0, c->stream>>>(
+            s.pr_shape, s.pr_rate, s.R, s.pr_prior_shape, s.pr_prior_rate, lgamma(s.pr_prior_shape),
+            c->elbo_blocks + (size_t)(slot + 2 + side) * per);
+        c->launches++;
+      }
+      if (c->bias) { // rows x 1 GPMatrix that never saw set_prior_rate: constant prior
+        elbo::GammaArgs b;
+        b.R = s.R; b.K = 1; b.ld = 1;
+        b.shape = s.b_shape; b.rate = s.b_rate; b.Ev = s.b_Ev; b.Elog = s.b_Elog;
+        b.rate_is_vector = 0;
+        b.sprior = s.bias_prior_shape; b.rprior = s.bias_prior_rate; b.lg_sprior = lgamma(s.bias_prior_shape);
+        b.pri_shape = nullptr; b.pri_rate = nullptr;
+        b.block_sums = c->elbo_blocks + (size_t)(slot + 4 + side) * per;
+        elbo::gamma_matrix_kernel<<<grid_for(s.R), elbo::kThreads, 0, c->stream>>>(b);
+        c->launches++;
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  std::vector<double> part((size_t)kElboLaunches * per);
+  CU(cudaMemcpyAsync(part.data(), c->elbo_blocks, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (double v : part) tot += v; // fixed order: launch by launch, block by block
+  *elbo_out = tot;
   return 0;
 }
 

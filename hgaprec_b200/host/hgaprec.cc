@@ -50,17 +50,22 @@ void HGAPRec::die(const char *what)
 HGAPRec::HGAPRec(Options &opt, Ratings &ratings)
     : opt_(opt), ratings_(ratings), n_(ratings.n()), m_(ratings.m()), k_(opt.k), iter_(0), start_time_(time(0)),
       st_(n_, m_, k_, opt.hier), rng_(0), prev_h_(0.0), nh_(0),
-      topn_by_user_(100), vf_(0), tf_(0), pf_(0), logf_(0), ctx_(0)
+      topn_by_user_(100), vf_(0), tf_(0), pf_(0), af_(0), logf_(0), ctx_(0)
 {
   // gsl_rng_alloc + gsl_rng_set(seed) only when the seed is non-zero (8-38); the
   // seed is a double truncated to unsigned long
   if (opt_.seed) rng_.set((unsigned long)opt_.seed);
   logf_ = fopen(out("/infer.log").c_str(), "a");
-  // the reference opens (and leaves empty) heldout/logl/ndcg/rmse as well (40-74)
-  const char *empties[] = { "/heldout.txt", "/logl.txt", "/ndcg.txt", "/rmse.txt" };
-  for (size_t i = 0; i < 4; ++i) {
+  // the reference opens (and leaves empty) heldout/ndcg/rmse as well (40-74)
+  const char *empties[] = { "/heldout.txt", "/ndcg.txt", "/rmse.txt" };
+  for (size_t i = 0; i < 3; ++i) {
     FILE *f = fopen(out(empties[i]).c_str(), "w");
     if (f) fclose(f);
+  }
+  af_ = fopen(out("/logl.txt").c_str(), "w"); // _af (56-60): one "%.5f" line per report window under -logl
+  if (!af_) {
+    printf("cannot open logl file:%s\n", strerror(errno));
+    exit(-1);
   }
   vf_ = fopen(out("/validation.txt").c_str(), "w");
   tf_ = fopen(out("/test.txt").c_str(), "w");
@@ -85,7 +90,7 @@ HGAPRec::HGAPRec(Options &opt, Ratings &ratings)
   cfg.n_items = m_;
   cfg.k = k_;
   cfg.flags = (opt_.hier ? HPF_HIER : 0u) | (opt_.bias ? HPF_BIAS : 0u) | (opt_.binary_data ? HPF_BINARY : 0u) |
-              (!opt_.vb ? HPF_JACOBI : 0u);
+              (!opt_.vb ? HPF_JACOBI : 0u) | (opt_.logl ? HPF_LOGL : 0u);
   cfg.device = opt_.device;
   if (hpf_create(&cfg, &ctx_) != 0) die("hpf_create");
 }
@@ -95,6 +100,7 @@ HGAPRec::~HGAPRec()
   if (vf_) fclose(vf_);
   if (tf_) fclose(tf_);
   if (pf_) fclose(pf_);
+  if (af_) fclose(af_);
   if (logf_) fclose(logf_);
   hpf_destroy(ctx_);
 }
@@ -187,7 +193,17 @@ void HGAPRec::report()
   compute_likelihood(false);
   save_model();
   compute_precision(false);
-  compute_itemrank(false);
+  if (opt_.hier || !opt_.bias) compute_itemrank(false); // vb_bias's report block has no compute_itemrank (1301-1310)
+  if (opt_.logl) logl();
+}
+
+// HGAPRec::logl (2160-2255): the sweep over the training nonzeros and the Gamma terms run on the device
+void HGAPRec::logl()
+{
+  double s = 0.0;
+  if (hpf_elbo(ctx_, &s) != 0) die("hpf_elbo");
+  fprintf(af_, "%.5f\n", s);
+  fflush(af_);
 }
 
 void HGAPRec::compute_likelihood(bool validation)

@@ -66,6 +66,7 @@ private:
   void compute_likelihood(bool validation);// src/hgaprec.cc:1439-1501
   void compute_precision(bool save_ranking_file); // src/hgaprec.cc:1703-1848
   void compute_itemrank(bool final);       // src/hgaprec.cc:1607-1701
+  void logl();                             // src/hgaprec.cc:2160-2255
   void save_model();                       // src/hgaprec.cc:2137-2158
   bool load_beta_and_theta();              // src/hgaprec.cc:2114-2135
   void do_on_stop();                       // src/hgaprec.cc:1572-1577
@@ -88,7 +89,7 @@ private:
   double prev_h_;
   int nh_;
   uint32_t topn_by_user_;
-  FILE *vf_, *tf_, *pf_, *logf_;
+  FILE *vf_, *tf_, *pf_, *af_, *logf_;
   hpf_ctx *ctx_;
 };
 

@@ -54,6 +54,10 @@ extern "C" {
 #define HPF_BINARY  4u /* -binary-data : likelihood form, src/hgaprec.cc:1557-1558    */
 #define HPF_JACOBI  8u /* -novb        : vb_bias() else-branch, src/hgaprec.cc:1276-1297
                           (ignored with HPF_HIER, as in the reference)                */
+#define HPF_LOGL   16u /* -logl        : keep what hpf_elbo() needs (src/main.cc:128-130,
+                          src/hgaprec.cc:1426-1427): a device copy of the CSR row pointer and,
+                          with HPF_HIER, the xi / eta sets as they were before each iteration.
+                          Changes no result of any other call.                         */
 
 /* which parameter set a get/set call addresses; names follow HGAPRec's members
  * (src/hgaprec.hh:105-115).  With HPF_HIER, THETA/BETA are _htheta/_hbeta
@@ -151,6 +155,17 @@ HPF_API int hpf_iterate(hpf_ctx *ctx, uint32_t n_iters);
 HPF_API int hpf_heldout_loglik(hpf_ctx *ctx, const uint32_t *u, const uint32_t *i,
                        const uint8_t *y, uint64_t npairs, double *sum_ll);
 
+/* HGAPRec::logl() (src/hgaprec.cc:2160-2255): the variational lower bound the reference appends
+ * to logl.txt in every report window under -logl -- the per-nonzero terms over the ctx's training
+ * matrix plus compute_elbo_term() of every parameter set (src/gpbase.hh:360-387, 717-741,
+ * 951-969).  Needs a ctx created with HPF_LOGL.  With HPF_HIER the Gamma terms of theta / beta
+ * use the rate priors the last iteration's set_prior_rate stored (src/gpbase.hh:163-173), so at
+ * least one hpf_iterate must have run since THETARATE / BETARATE were set (the reference only
+ * calls logl() inside the loop).  Multi-GPU: the value is this rank's part -- its users'
+ * nonzeros and user-side sets, plus the (replicated) item-side sets on rank 0 only -- so the sum
+ * over the ranks is the ELBO of the whole problem. */
+HPF_API int hpf_elbo(hpf_ctx *ctx, double *elbo_out);
+
 /* compute_precision's scoring pass (src/hgaprec.cc:1703-1763, 1969-1991): for
  * each listed local user score every item with E[theta_u].E[beta_i] (+biases),
  * force the items of the user's exclusion list (train U validation) to 0.0 --
@@ -161,11 +176,6 @@ HPF_API int hpf_topn(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
              const uint64_t *excl_ptr, const uint32_t *excl_idx, uint32_t topn,
              uint32_t *items_out, float *scores_out);
 
-/* Multi-GPU (one process per GPU, users sharded, beta replicated): join an NCCL
- * communicator.  Rank 0 obtains an id with hpf_comm_unique_id and hands it to
- * the other ranks by any means (bench.py uses torch.distributed).  After this,
- * hpf_iterate all-reduces the item-side accumulators once per iteration and
- * hpf_heldout_loglik stays rank-local. */
 /* compute_itemrank's ranking (src/hgaprec.cc:1607-1701): for each listed local
  * user and each of its query items (query_ptr: nu+1 entries into query_idx; the
  * reference asks for the user's test items), the 0-based position of the item in
@@ -185,6 +195,11 @@ HPF_API int hpf_item_ranks(hpf_ctx *ctx, const uint32_t *users, uint32_t nu,
 HPF_API int hpf_partition_users(const uint64_t *row_ptr, uint32_t n_users, uint32_t nranks,
                         uint32_t *first_user_out);
 
+/* Multi-GPU (one process per GPU, users sharded, beta replicated): join an NCCL
+ * communicator.  Rank 0 obtains an id with hpf_comm_unique_id and hands it to
+ * the other ranks by any means (bench.py uses torch.distributed).  After this,
+ * hpf_iterate all-reduces the item-side accumulators once per iteration and
+ * hpf_heldout_loglik stays rank-local. */
 #define HPF_COMM_ID_BYTES 128
 HPF_API int hpf_comm_unique_id(void *id_out, size_t id_bytes);
 HPF_API int hpf_comm_init(hpf_ctx *ctx, int rank, int nranks, const void *id, size_t id_bytes);

@@ -2,7 +2,8 @@
 """Generate tests/golden/cli_<mode>/ from the UNMODIFIED reference command line.
 
 Runs oracle/_ref/hgaprec_ref (src/main.cc ... built by oracle/Makefile) on the
-data set of tests/golden/ref_<mode>.npz, first a fit (-rfreq 2 -max-iterations 4),
+data set of tests/golden/ref_<mode>.npz, first a fit (-rfreq 2 -max-iterations 4 -logl:
+logl.txt gets one ELBO line per report window, nothing else changes),
 then -gen-ranking from inside the fit's output directory,
 and keeps the report files the new driver has to reproduce: validation.txt,
 test.txt, max.txt, precision.txt, the model TSVs and ranking.tsv.  Only runnable
@@ -24,7 +25,7 @@ import util  # noqa: E402
 from oracle import hpf_oracle as O  # noqa: E402
 
 MODES = {"hier": ["-hier"], "hier_bias": ["-hier", "-bias"]}
-KEEP = ("validation.txt", "test.txt", "max.txt", "precision.txt", "param.txt", "byusers.tsv", "byitems.tsv")
+KEEP = ("validation.txt", "test.txt", "max.txt", "precision.txt", "param.txt", "byusers.tsv", "byitems.tsv", "logl.txt")
 
 
 def main():
@@ -41,7 +42,7 @@ def main():
             data = os.path.join(tmp, "data")
             util.write_dataset(g, data)
             base = [O.REF_BINARY, "-dir", data, "-n", str(n), "-m", str(m), "-k", str(k), "-seed", "777", "-label", "g"] + sw
-            subprocess.check_call(base + ["-rfreq", "2", "-max-iterations", "4"], cwd=tmp, stdout=subprocess.DEVNULL)
+            subprocess.check_call(base + ["-rfreq", "2", "-max-iterations", "4", "-logl"], cwd=tmp, stdout=subprocess.DEVNULL)
             fit = [d for d in os.listdir(tmp) if d.startswith("n%d-" % n)]
             assert len(fit) == 1, fit
             fitdir = os.path.join(tmp, fit[0])
@@ -54,7 +55,8 @@ def main():
             for f in ("precision.txt", "meanrank.txt"):
                 shutil.copy(os.path.join(rank, f), os.path.join(dst, "rank", f))
             for f in ("ranking.tsv", "itemrank.tsv"):
-                with open(os.path.join(rank, f), "rb") as fi, gzip.open(os.path.join(dst, "rank", f + ".gz"), "wb") as fo:
+                with open(os.path.join(rank, f), "rb") as fi, open(os.path.join(dst, "rank", f + ".gz"), "wb") as raw, \
+                        gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as fo:  # mtime=0: reruns are byte-identical
                     fo.write(fi.read())
         print("wrote", dst, sorted(os.listdir(os.path.join(dst, "fit"))), sorted(os.listdir(os.path.join(dst, "rank"))))
 

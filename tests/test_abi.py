@@ -21,7 +21,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for s in ("hpf_create", "hpf_destroy", "hpf_set_ratings_csr", "hpf_set_state", "hpf_get_state",
-              "hpf_iterate", "hpf_heldout_loglik", "hpf_topn", "hpf_item_ranks", "hpf_partition_users", "hpf_comm_init",
+              "hpf_iterate", "hpf_heldout_loglik", "hpf_elbo", "hpf_topn", "hpf_item_ranks", "hpf_partition_users", "hpf_comm_init",
               "hpf_last_error"):
         assert s in syms
 

@@ -60,6 +60,70 @@ def test_oracle_elbo_matches_reference_logl(mode, t):
     assert step.elbo(rp, ci, y) == iterated.elbo(rp, ci, y)
 
 
+def _device_formulas_elbo(s, rp, ci, y, pri):
+    """numpy mirror of hgaprec_b200/csrc/hpf_elbo.cuh (same algebra, fp32-stored state, fp64 sums): per nonzero
+    y^2 (logsumexp(x) - log y) - E[theta].E[beta] (- bias expectations); Gamma terms element by element with the
+    hier rate prior rebuilt from the previous xi / eta (shape, rate)."""
+    from scipy.special import digamma, gammaln
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)
+    P = {g: {f: f32(s.p[g][f]) for f in O.FIELDS} for g in s.p}
+    u = np.repeat(np.arange(s.n), np.diff(rp.astype(np.int64)))
+    i = ci.astype(np.int64)
+    yy = np.ones(len(i)) if y is None else y.astype(np.float64)
+    x = P["theta"]["Elogv"][u] + P["beta"]["Elogv"][i]
+    sub = (P["theta"]["Ev"][u] * P["beta"]["Ev"][i]).sum(1)
+    if s.bias:
+        x = np.concatenate([x, P["thetabias"]["Elogv"][u, None], P["betabias"]["Elogv"][i, None]], axis=1)
+        sub = sub + P["thetabias"]["Ev"][u] + P["betabias"]["Ev"][i]
+    mx = x.max(1)
+    lse = mx + np.log(np.exp(x - mx[:, None]).sum(1))
+    tot = float((yy * yy * (lse - np.log(yy)) - sub).sum())
+
+    def gamma_terms(g, rate, rp_, lrp_):  # gamma_matrix_kernel
+        a, b = np.maximum(g["shape"], 1e-30), np.maximum(rate, 1e-30)
+        t = 0.3 * lrp_ + (0.3 - 1) * g["Elogv"] - (rp_ * g["Ev"] + gammaln(0.3))
+        t = t - (a * np.log(b) + (a - 1) * g["Elogv"]) + b * g["Ev"] + gammaln(a)
+        return float(t.sum())
+
+    for gname, bname, k in (("theta", "thetarate", 0), ("beta", "betarate", 2)):
+        g = P[gname]
+        if s.hier:
+            pa, pb = np.maximum(f32(pri[k]), 1e-30), np.maximum(f32(pri[k + 1]), 1e-30)  # previous (shape, rate)
+            tot += gamma_terms(g, g["rate"], (pa / pb)[:, None], (digamma(pa) - np.log(pb))[:, None])
+            a, b = np.maximum(P[bname]["shape"], 1e-30), np.maximum(P[bname]["rate"], 1e-30)  # gamma_array_kernel
+            ev, el = a / b, digamma(a) - np.log(b)
+            tot += float((0.3 * np.log(0.3) + (0.3 - 1) * el - (0.3 * ev + gammaln(0.3))
+                          - (a * np.log(b) + (a - 1) * el) + b * ev + gammaln(a)).sum())
+        else:
+            tot += gamma_terms(g, g["rate"][None, :], 0.3, np.log(0.3))
+    if s.bias:
+        for gname in ("thetabias", "betabias"):
+            g = P[gname]
+            tot += gamma_terms(g, g["rate"], 0.3, np.log(0.3))
+    return tot
+
+
+@pytest.mark.parametrize("mode", util.MODES)
+def test_device_elbo_algebra_matches_reference_logl(mode):
+    """hpf_elbo.cuh does not walk the reference's literal sum: it uses y^2 (logsumexp - log y) per nonzero and
+    rebuilds the hier rate priors from the previous xi / eta (shape, rate).  That algebra, on fp32-rounded state,
+    must reproduce the reference's own logl() value (CPU check of the formulas; the kernels are checked on the GPU)."""
+    g = util.load_golden(mode)
+    rp, ci, y = g["csr.row_ptr"], g["csr.col_idx"], g["csr.y"]
+    prev = util.golden_state(g, 0)
+    done = 0
+    for t in (1, 3):
+        if t - done > 1:
+            prev.iterate(rp, ci, y, t - done - 1)
+        pri = (prev.p["thetarate"]["shape"], prev.p["thetarate"]["rate"], prev.p["betarate"]["shape"], prev.p["betarate"]["rate"])
+        pri = tuple(a.copy() for a in pri)
+        prev.iterate(rp, ci, y, 1)
+        done = t
+        ref = float(g["T%d/elbo" % t][0])
+        got = _device_formulas_elbo(prev, rp, ci, y, pri)
+        assert abs(got - ref) <= 2e-7 * abs(ref), (mode, t, got, ref)
+
+
 @pytest.mark.parametrize("mode", ("hier", "bpf_bias"))
 def test_oracle_init_matches_reference_golden(mode):
     g = util.load_golden(mode)
