@@ -2,7 +2,7 @@
 // maps, the held-out maps and the start state) without touching a GPU, so the
 // CPU test-suite can compare the host logic with the reference's own dumps.
 //   hgaprec_hostcheck -dir D -n N -m M -k K [-hier] [-bias] [-binary-data]
-//                     [-rating-threshold V] [-seed S] -out FILE
+//                     [-rating-threshold V] [-seed S] [-csr-cache] -out FILE
 // FILE is a flat tagged container ("HPFDUMP1": name, dtype, dims, data per record)
 // that the test-suite reads back.
 #include <stdio.h>
@@ -71,13 +71,15 @@ int main(int argc, char **argv)
     else if (!strcmp(a, "-bias")) o.bias = true;
     else if (!strcmp(a, "-binary-data")) o.binary_data = true;
     else if (!strcmp(a, "-novb")) o.vb = false;
+    else if (!strcmp(a, "-csr-cache")) o.csr_cache = true;
     else if (!strcmp(a, "-out")) outp = NEXT;
     else { fprintf(stderr, "unknown option %s\n", a); return 2; }
     #undef NEXT
   }
   Ratings ratings(o.n, o.m, o.binary_data, o.rating_threshold);
   std::string err;
-  if (!ratings.read_train(o.dir, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  if (!ratings.read_train(o.dir, &err, o.csr_cache)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  if (o.csr_cache) printf("csr cache: %s\n", ratings.cache_note().c_str());
   HeldoutMap val, tst;
   if (!ratings.read_heldout(o.dir + "/validation.tsv", &val, &err) || !ratings.read_heldout(o.dir + "/test.tsv", &tst, &err)) {
     fprintf(stderr, "%s\n", err.c_str());
@@ -102,6 +104,13 @@ int main(int argc, char **argv)
   d1[0] = y.size(); put(f, "csr.y", 2, y.data(), 1, d1);
   d1[0] = n; put(f, "seq2user", 1, ratings.seq2user().data(), 4, d1);
   d1[0] = m; put(f, "seq2movie", 1, ratings.seq2item().data(), 4, d1);
+  {
+    std::vector<uint32_t> deg(m);
+    std::vector<uint64_t> tot(m);
+    for (uint32_t i = 0; i < m; ++i) { deg[i] = ratings.item_degree(i); tot[i] = ratings.item_total(i); }
+    d1[0] = m; put(f, "item_degree", 1, deg.data(), 4, d1);
+    put(f, "item_total", 3, tot.data(), 8, d1);
+  }
   put_map(f, "validation", val);
   put_map(f, "test", tst);
   const std::string tn = o.hier ? "htheta" : "theta", bn = o.hier ? "hbeta" : "beta";

@@ -61,6 +61,7 @@ int main(int argc, char **argv)
     else if (!strcmp(a, "-gen-ranking")) o.gen_ranking = true;
     else if (!strcmp(a, "-rating-threshold")) o.rating_threshold = atoi(NEXT);
     else if (!strcmp(a, "-device")) o.device = atoi(NEXT);
+    else if (!strcmp(a, "-csr-cache")) o.csr_cache = true;
     else if (!strcmp(a, "-load") || !strcmp(a, "-nmi") || !strcmp(a, "-wals_l") || !strcmp(a, "-wals_C")) (void)NEXT; // parsed, unused
     else if (!strcmp(a, "-batch") || !strcmp(a, "-p") || !strcmp(a, "-strid") || !strcmp(a, "-gen-heldout") ||
              !strcmp(a, "-pred-accuracy") || !strcmp(a, "-gt-accuracy") || !strcmp(a, "-netflix") || !strcmp(a, "-mendeley") ||
@@ -106,10 +107,11 @@ int main(int argc, char **argv)
   fprintf(stdout, "+ reading ratings dataset from %s\n", o.dir.c_str());
   fflush(stdout);
   std::string err;
-  if (!ratings.read_train(o.dir, &err)) {
+  if (!ratings.read_train(o.dir, &err, o.csr_cache)) {
     fprintf(stderr, "error: %s", err.c_str());
     exit(-1);
   }
+  if (o.csr_cache) fprintf(stdout, "+ csr cache: %s\n", ratings.cache_note().c_str());
   ratings.write_marginals(o.prefix);
   fprintf(pl, "training ratings: %d\n", (int)ratings.nratings());
   fprintf(pl, "statistics: read %d users, %d movies, %d ratings\n", ratings.n(), ratings.m(), (int)ratings.nratings());

@@ -2,8 +2,144 @@
 
 #include <errno.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace hpfhost {
+
+// ---- binary cache of the parsed training matrix --------------------------------
+namespace {
+
+struct CacheHeader {
+  char magic[8];                 // "HPFCSR01"
+  uint32_t max_users, max_items; // the -n / -m caps the parse ran under
+  uint32_t binary, threshold;    // -binary-data, -rating-threshold
+  uint32_t n, m;                 // users / items that received a sequence number
+  uint64_t nratings;             // lines kept == CSR entries
+  uint64_t tsv_size;             // train.tsv the cache was made from
+  int64_t tsv_mtime_s, tsv_mtime_ns;
+  uint64_t checksum;             // over the payload that follows the header
+};
+
+// 64-bit FNV-1a over 8-byte words (tail bytes one by one)
+uint64_t mix(uint64_t h, const void *data, size_t bytes)
+{
+  const unsigned char *p = (const unsigned char *)data;
+  size_t i = 0;
+  for (; i + 8 <= bytes; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 1099511628211ull;
+  }
+  for (; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+const uint64_t kMixSeed = 14695981039346656037ull;
+
+bool stat_tsv(const std::string &tsv, CacheHeader *h)
+{
+  struct stat sb;
+  if (stat(tsv.c_str(), &sb) != 0) return false;
+  h->tsv_size = (uint64_t)sb.st_size;
+  h->tsv_mtime_s = (int64_t)sb.st_mtim.tv_sec;
+  h->tsv_mtime_ns = (int64_t)sb.st_mtim.tv_nsec;
+  return true;
+}
+
+template <class T> bool read_vec(FILE *f, std::vector<T> *v, size_t count, uint64_t *h)
+{
+  v->resize(count);
+  if (count && fread(v->data(), sizeof(T), count, f) != count) return false;
+  *h = mix(*h, v->data(), count * sizeof(T));
+  return true;
+}
+template <class T> bool write_vec(FILE *f, const std::vector<T> &v, uint64_t *h)
+{
+  *h = mix(*h, v.data(), v.size() * sizeof(T));
+  return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size();
+}
+
+} // namespace
+
+bool Ratings::load_cache(const std::string &tsv, const std::string &cache)
+{
+  FILE *f = fopen(cache.c_str(), "rb");
+  if (!f) return false;
+  CacheHeader h, now;
+  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "HPFCSR01", 8) == 0 && stat_tsv(tsv, &now) &&
+            h.tsv_size == now.tsv_size && h.tsv_mtime_s == now.tsv_mtime_s && h.tsv_mtime_ns == now.tsv_mtime_ns &&
+            h.max_users == max_users_ && h.max_items == max_items_ && h.binary == (binary_ ? 1u : 0u) &&
+            h.threshold == threshold_ && h.n <= max_users_ && h.m <= max_items_;
+  if (ok) { // the header must account for every byte of the file before anything is sized from it
+    struct stat sb;
+    const uint64_t want = sizeof h + 4ull * h.n + 4ull * h.m + 8ull * ((uint64_t)h.n + 1) + 5ull * h.nratings;
+    ok = fstat(fileno(f), &sb) == 0 && (uint64_t)sb.st_size == want;
+  }
+  std::vector<uint32_t> s2u, s2i, col;
+  std::vector<uint64_t> rp;
+  std::vector<uint8_t> val;
+  uint64_t sum = kMixSeed;
+  ok = ok && read_vec(f, &s2u, h.n, &sum) && read_vec(f, &s2i, h.m, &sum) && read_vec(f, &rp, (size_t)h.n + 1, &sum) &&
+       rp[0] == 0 && rp[h.n] == h.nratings && read_vec(f, &col, h.nratings, &sum) && read_vec(f, &val, h.nratings, &sum) &&
+       sum == h.checksum && fgetc(f) == EOF;
+  fclose(f);
+  if (!ok) return false;
+  for (uint32_t u = 0; u < h.n; ++u)
+    if (rp[u + 1] < rp[u]) return false;
+  for (uint64_t j = 0; j < h.nratings; ++j)
+    if (col[j] >= h.m) return false;
+  seq2user_.swap(s2u);
+  seq2item_.swap(s2i);
+  user2seq_.clear(); item2seq_.clear();
+  user2seq_.reserve(h.n); item2seq_.reserve(h.m);
+  for (uint32_t u = 0; u < h.n; ++u) user2seq_[seq2user_[u]] = u;
+  for (uint32_t i = 0; i < h.m; ++i) item2seq_[seq2item_[i]] = i;
+  items_.assign(h.n, std::vector<uint32_t>());
+  vals_.assign(h.n, std::vector<uint8_t>());
+  for (uint32_t u = 0; u < h.n; ++u) {
+    items_[u].assign(col.begin() + rp[u], col.begin() + rp[u + 1]);
+    vals_[u].assign(val.begin() + rp[u], val.begin() + rp[u + 1]);
+  }
+  nratings_ = h.nratings;
+  finalize(); // values are already fixed up; this rebuilds the per-item degree and total
+  return true;
+}
+
+void Ratings::save_cache(const std::string &tsv, const std::string &cache)
+{
+  CacheHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, "HPFCSR01", 8);
+  if (!stat_tsv(tsv, &h)) { cache_note_ = "not written: cannot stat " + tsv; return; }
+  h.max_users = max_users_; h.max_items = max_items_;
+  h.binary = binary_ ? 1u : 0u; h.threshold = threshold_;
+  h.n = n(); h.m = m(); h.nratings = nratings_;
+  std::vector<uint64_t> rp(n() + 1, 0);
+  std::vector<uint32_t> col;
+  std::vector<uint8_t> val;
+  col.reserve(nratings_); val.reserve(nratings_);
+  for (uint32_t u = 0; u < n(); ++u) {
+    col.insert(col.end(), items_[u].begin(), items_[u].end());
+    val.insert(val.end(), vals_[u].begin(), vals_[u].end());
+    rp[u + 1] = col.size();
+  }
+  char tmp[64];
+  snprintf(tmp, sizeof tmp, ".tmp.%ld", (long)getpid());
+  const std::string part = cache + tmp; // written aside, renamed when complete: a reader never sees half a cache
+  FILE *f = fopen(part.c_str(), "wb");
+  if (!f) { cache_note_ = "not written: cannot create " + part + ": " + strerror(errno); return; }
+  uint64_t sum = kMixSeed;
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && write_vec(f, seq2user_, &sum) && write_vec(f, seq2item_, &sum) &&
+            write_vec(f, rp, &sum) && write_vec(f, col, &sum) && write_vec(f, val, &sum);
+  h.checksum = sum;
+  ok = ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(&h, sizeof h, 1, f) == 1;
+  ok = (fclose(f) == 0) && ok;
+  if (ok && rename(part.c_str(), cache.c_str()) == 0) cache_note_ = "written " + cache;
+  else {
+    cache_note_ = "not written: " + std::string(strerror(errno));
+    remove(part.c_str());
+  }
+}
 
 // one unsigned decimal (strtoul-like: optional sign, wraps modulo 2^32); false at end of input
 bool TripleReader::number(uint32_t *out)
@@ -26,9 +162,15 @@ bool TripleReader::number(uint32_t *out)
   return true;
 }
 
-bool Ratings::read_train(const std::string &dir, std::string *err)
+bool Ratings::read_train(const std::string &dir, std::string *err, bool use_cache)
 {
   const std::string path = dir + "/train.tsv";
+  const std::string cache = path + ".hpfcsr";
+  cache_note_.clear();
+  if (use_cache && load_cache(path, cache)) {
+    cache_note_ = "loaded " + cache;
+    return true;
+  }
   FILE *f = fopen(path.c_str(), "r");
   if (!f) {
     *err = "cannot open file " + path + ": " + strerror(errno);
@@ -69,6 +211,7 @@ bool Ratings::read_train(const std::string &dir, std::string *err)
   }
   fclose(f);
   finalize();
+  if (use_cache) save_cache(path, cache);
   return true;
 }
 

@@ -14,6 +14,13 @@
 // Unlike the reference (fscanf + a std::map node per rating, minutes and tens of
 // GB at Netflix scale) the reader parses the file from a large buffer and keeps
 // 5 bytes per rating: per user the item list and a parallel value list.
+//
+// Binary cache (the reference has no counterpart): with use_cache the parsed
+// training matrix -- id maps, CSR, post-fix-up values -- is kept next to the data as
+// <dir>/train.tsv.hpfcsr and reloaded by the next run instead of parsing the text again.  A cache is
+// only used when it was written for the same train.tsv (size and modification time), the same -n / -m
+// caps and the same -binary-data / -rating-threshold, and its checksum holds; otherwise the text is
+// parsed and the cache rewritten.  Whatever is loaded is bit-identical to what the parser builds.
 #ifndef HPF_HOST_RATINGS_HH
 #define HPF_HOST_RATINGS_HH
 #include <stdint.h>
@@ -58,7 +65,9 @@ public:
       : max_users_(max_users), max_items_(max_items), binary_(binary), threshold_(rating_threshold), nratings_(0) {}
 
   // train.tsv -> adjacency in file order.  Returns false if the file cannot be read.
-  bool read_train(const std::string &dir, std::string *err);
+  bool read_train(const std::string &dir, std::string *err, bool use_cache = false);
+  // what the cache did for the last read_train: "", "loaded <path>", "written <path>" or "not written: <why>"
+  const std::string &cache_note() const { return cache_note_; }
   // validation.tsv / test.tsv -> map; unseen users / items are skipped
   bool read_heldout(const std::string &path, HeldoutMap *out, std::string *err) const;
   // test_users.tsv -> set of user seqs (Ratings::read_test_users, src/ratings.cc:273-292)
@@ -77,6 +86,7 @@ public:
   uint32_t value_at(uint32_t u, size_t j) const { return vals_[u][j]; }
   // Ratings::get_users(m)->size(): lines that named the item
   uint32_t item_degree(uint32_t i) const { return item_degree_[i]; }
+  uint64_t item_total(uint32_t i) const { return item_total_[i]; } // sum of the item's ratings (byitems.tsv)
   // Ratings::r(n, m): 0 when absent (src/ratings.hh:153-165)
   uint32_t r(uint32_t u, uint32_t i) const
   {
@@ -97,6 +107,9 @@ public:
 private:
   uint32_t rating_class(uint32_t v) const { return binary_ ? (v >= threshold_ ? 1u : 0u) : v; }
   void finalize(); // repeated (user, item) lines take the last value; per-item degree and rating total
+  bool load_cache(const std::string &tsv, const std::string &cache);
+  void save_cache(const std::string &tsv, const std::string &cache);
+  std::string cache_note_;
   uint32_t max_users_, max_items_;
   bool binary_;
   uint32_t threshold_;

@@ -79,3 +79,78 @@ def test_reader_edge_cases(hostcheck, tmp_path):
     np.testing.assert_array_equal(d["csr.y"], [5, 1, 1, 4, 4])
     np.testing.assert_array_equal(d["validation.u"], [0])
     np.testing.assert_array_equal(d["test.y"], [1])
+
+
+def _run_check(hostcheck, data, out, *extra):
+    p = subprocess.run([hostcheck, "-dir", data, "-out", out] + list(extra), check=True, capture_output=True, text=True)
+    return p.stdout
+
+
+@pytest.mark.parametrize("mode", ("hier", "hier_binary"))
+def test_csr_cache_reload_is_bit_identical_and_invalidates(hostcheck, tmp_path, mode):
+    """-csr-cache: the second run loads <dir>/train.tsv.hpfcsr instead of parsing the text and
+    hands over exactly the same CSR, id maps, held-out maps, item marginals and start state; a cache made for another
+    train.tsv, other -n/-m caps or another rating class is not used; a damaged cache is ignored."""
+    g = util.load_golden(mode)
+    n, m, k = (int(v) for v in g["T0/meta"][:3])
+    data = str(tmp_path / "data")
+    util.write_dataset(g, data, lift=3 if "binary" in mode else 0)
+    # a repeated (user, item) line: the cache has to carry the fixed-up values
+    lines = open(os.path.join(data, "train.tsv")).read().splitlines()
+    a, b, _ = lines[0].split("\t")
+    lines.insert(5, "%s\t%s\t4" % (a, b))
+    open(os.path.join(data, "train.tsv"), "w").write("\n".join(lines) + "\n")
+    base = ["-n", str(n), "-m", str(m), "-k", str(k), "-seed", "777"] + SWITCHES[mode]
+    cache = os.path.join(data, "train.tsv.hpfcsr")
+    plain, first, second = (str(tmp_path / f) for f in ("plain.bin", "first.bin", "second.bin"))
+
+    _run_check(hostcheck, data, plain, *base)
+    assert not os.path.exists(cache)                      # nothing is written without the flag
+    assert "csr cache: written" in _run_check(hostcheck, data, first, *(base + ["-csr-cache"]))
+    assert "csr cache: loaded" in _run_check(hostcheck, data, second, *(base + ["-csr-cache"]))
+    assert open(plain, "rb").read() == open(first, "rb").read() == open(second, "rb").read()
+    assert [f for f in os.listdir(data) if ".tmp." in f] == []
+
+    other = str(tmp_path / "other.bin")
+    # other caps / other rating class: parsed again (and the cache replaced)
+    assert "csr cache: written" in _run_check(hostcheck, data, other, "-n", str(n - 1), "-m", str(m), "-k", str(k), "-csr-cache")
+    assert "csr cache: written" in _run_check(hostcheck, data, other, *(base + ["-csr-cache"]))
+    if "binary" in mode:
+        assert "csr cache: written" in _run_check(hostcheck, data, other, "-n", str(n), "-m", str(m), "-k", str(k), "-hier",
+                                                  "-binary-data", "-rating-threshold", "4", "-csr-cache")
+        assert "csr cache: written" in _run_check(hostcheck, data, other, *(base + ["-csr-cache"]))
+    # damaged payload (checksum), truncated file, garbage: ignored, parsed again, result unchanged
+    blob = bytearray(open(cache, "rb").read())
+    for damage in ("flip", "truncate", "garbage"):
+        bad = bytearray(blob)
+        if damage == "flip":
+            bad[len(bad) // 2] ^= 0x40
+        elif damage == "truncate":
+            bad = bad[:-7]
+        else:
+            bad = bytearray(b"not a cache")
+        open(cache, "wb").write(bytes(bad))
+        st = os.stat(os.path.join(data, "train.tsv"))
+        assert "csr cache: written" in _run_check(hostcheck, data, other, *(base + ["-csr-cache"])), damage
+        assert open(other, "rb").read() == open(plain, "rb").read(), damage
+        assert os.stat(os.path.join(data, "train.tsv")).st_mtime_ns == st.st_mtime_ns
+    # train.tsv changed (one more line): the old cache is not used, the new result differs
+    open(os.path.join(data, "train.tsv"), "a").write(lines[1] + "\n")
+    assert "csr cache: written" in _run_check(hostcheck, data, other, *(base + ["-csr-cache"]))
+    fresh = str(tmp_path / "fresh.bin")
+    _run_check(hostcheck, data, fresh, *base)
+    assert open(other, "rb").read() == open(fresh, "rb").read() != open(plain, "rb").read()
+
+
+def test_csr_cache_in_a_read_only_directory_is_not_an_error(hostcheck, tmp_path):
+    g = util.load_golden("bpf")
+    n, m, k = (int(v) for v in g["T0/meta"][:3])
+    data = str(tmp_path / "data")
+    util.write_dataset(g, data)
+    os.chmod(data, 0o555)
+    try:
+        out = _run_check(hostcheck, data, str(tmp_path / "o.bin"), "-n", str(n), "-m", str(m), "-k", str(k), "-csr-cache")
+        if os.geteuid() != 0:  # root writes anywhere
+            assert "csr cache: not written" in out
+    finally:
+        os.chmod(data, 0o755)
