@@ -125,9 +125,14 @@ HPF_API const char *hpf_last_error(const hpf_ctx *ctx);
  * loop walks it: row u lists Ratings::get_movies(u) in file order and y holds
  * Ratings::r(u, i) (src/hgaprec.cc:1340-1345, src/ratings.hh:153-181).
  * row_ptr: n_users+1 entries; col_idx, y: row_ptr[n_users] entries;
- * y == NULL means every rating is 1 (-binary-data).  Replaces the Ratings
- * adjacency-list iterator (src/env.hh:36-37).  May be called again to replace
- * the matrix. */
+ * y == NULL means every rating is 1 (-binary-data).  Ratings are >= 1: the
+ * reference's reader drops class-0 lines (src/ratings.hh:191-197), and a value
+ * that wrapped to 0 in its uint8 is walked by its loop as a 1 (only y > 1 scales,
+ * src/hgaprec.cc:1355-1356) -- pass 1 for it, as hgaprec_b200/host does; an entry
+ * with y == 0 contributes nothing here.  A (user, item) pair may be listed more
+ * than once; every entry is processed, as the reference walks every line.
+ * Replaces the Ratings adjacency-list iterator (src/env.hh:36-37).  May be called
+ * again to replace the matrix. */
 HPF_API int hpf_set_ratings_csr(hpf_ctx *ctx, const uint64_t *row_ptr,
                         const uint32_t *col_idx, const uint8_t *y);
 

@@ -153,3 +153,41 @@ def test_cli_logl_file_matches_reference(tmp_path, mode, switches):
     want = np.loadtxt(os.path.join(gold, "fit", "logl.txt"))
     assert got.shape == want.shape == (3,)  # iterations 0, 2, 4
     np.testing.assert_allclose(got, want, rtol=TOL_ELBO_REL)
+
+
+@pytest.mark.parametrize("flags", [H.HIER | H.BIAS, 0])
+def test_two_gpu_elbo_parts_add_up(flags):
+    """Users sharded over two GPUs: each rank returns its users' terms, rank 0 adds the replicated item side; the sum
+    is the ELBO of the whole problem (include/hpf_cuda.h).  Needs two devices (`gpurun --gpus 2`)."""
+    import threading
+    import torch
+    if not (torch.cuda.is_available() and torch.cuda.device_count() >= 2):
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 3000, 900, 120000, 50, 2
+    d = synth.make_ratings(n, m, nnz, seed=31, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(32)
+    ref = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8).elbo(d["row_ptr"], d["col_idx"], d["y"])
+    bounds = H.partition_users(d["row_ptr"], 2)
+    rp = d["row_ptr"].astype(np.int64)
+    uid = H.comm_unique_id()
+    part, errs = [None, None], []
+
+    def worker(r):
+        try:
+            lo, hi = int(bounds[r]), int(bounds[r + 1])
+            with H.Engine(hi - lo, m, k, flags=flags | H.LOGL, device=r, n_users_global=n) as e:
+                e.comm_init(r, 2, uid)
+                e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], d["y"][rp[lo]:rp[hi]])
+                util.push_state(e, s, users=np.arange(lo, hi))
+                e.iterate(iters)
+                part[r] = e.elbo()
+        except Exception as ex:  # surfaced in the main thread
+            errs.append(ex)
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    assert abs(part[0] + part[1] - ref) <= TOL_ELBO_REL * abs(ref), (part, ref)
