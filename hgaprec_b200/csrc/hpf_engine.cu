@@ -214,6 +214,10 @@ struct hpf_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // HPF_AR_OVERLAP=1 (opt-in): the all-reduce of [T_beta | Tb_beta] runs on its own stream under the theta update
+  bool ar_overlap = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_tbeta = nullptr, ev_ar = nullptr;
   // stats
   uint64_t launches = 0, iterations = 0;
   float last_ms = 0.f, last_topn_ms = 0.f;
@@ -943,12 +947,31 @@ int one_iteration(hpf_ctx *c)
     }
     CU(cudaMemcpyAsync(c->colsum_theta_old, c->th.colsum, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
   }
+  // HPF_AR_OVERLAP: T_beta and Tb_beta are final here, sum_u E[theta] is not.  Their all-reduce starts now on the
+  // second stream and runs under the theta update (which touches neither; its column sums land in the last Kp
+  // floats of the block, outside this reduction); the Kp column sums follow on the main stream.  The two
+  // reductions never overlap each other: each waits for the other's stream through an event.
+  const bool overlap = c->ar_overlap && c->nranks > 1 && !c->jacobi && !c->profiling;
+  if (overlap) {
+    CU(cudaEventRecord(c->ev_tbeta, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_tbeta, 0));
+    int rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count - c->Kp, ncclFloat32, ncclSum, c->comm, c->comm_stream);
+    if (rc != ncclSuccess)
+      return fail(c, HPF_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    CU(cudaEventRecord(c->ev_ar, c->comm_stream));
+  }
   // theta: rate from the old beta column sums (Gauss-Seidel and Jacobi alike)
   TRY(launch_update(c, c->th, c->be.colsum, (double)c->cfg.n_items));
   MARK(4);
   if (c->nranks > 1) {
-    // [T_beta | Tb_beta | colsum_theta] summed over the user shards, in place
-    int rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count, ncclFloat32, ncclSum, c->comm, c->stream);
+    int rc;
+    if (overlap) {
+      CU(cudaStreamWaitEvent(c->stream, c->ev_ar, 0));
+      rc = g_nccl.AllReduce(c->th.colsum, c->th.colsum, c->Kp, ncclFloat32, ncclSum, c->comm, c->stream);
+    } else {
+      // [T_beta | Tb_beta | colsum_theta] summed over the user shards, in place
+      rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count, ncclFloat32, ncclSum, c->comm, c->stream);
+    }
     if (rc != ncclSuccess)
       return fail(c, HPF_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     c->th_colsum_global = true;
@@ -1097,7 +1120,11 @@ void hpf_destroy(hpf_ctx *c)
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->ev_tbeta) cudaEventDestroy(c->ev_tbeta);
+  if (c->ev_ar) cudaEventDestroy(c->ev_ar);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (auto &p : c->allocs) cudaFree(p.first);
   if (c->dev_arena.base) cudaFree(c->dev_arena.base);
   if (c->dev_arena2.base) cudaFree(c->dev_arena2.base);
@@ -1910,6 +1937,12 @@ int hpf_comm_init(hpf_ctx *c, int rank, int nranks, const void *id, size_t id_by
   int rc = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
   if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   c->rank = rank; c->nranks = nranks;
+  if (const char *e = getenv("HPF_AR_OVERLAP")) c->ar_overlap = atoi(e) != 0 && nranks > 1;
+  if (c->ar_overlap && !c->comm_stream) {
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_tbeta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming));
+  }
   return 0;
 }
 

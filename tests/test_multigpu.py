@@ -166,3 +166,46 @@ def test_two_gpu_shards_match_single_gpu_and_oracle(flags):
         one = util.pull_state(e, s)
     bad = util.compare_states(got, one, rel=1e-5, elog_abs=1e-5)
     assert not bad, bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [H.HIER | H.BIAS, 0])
+def test_two_gpu_allreduce_overlap_is_bitwise_the_default(monkeypatch, flags):
+    """HPF_AR_OVERLAP=1 (opt-in): [T_beta | Tb_beta] reduced on a second stream under the theta update, the Kp column
+    sums afterwards.  Same operands, two ranks: every sum is a + b either way, so the state must not change by a bit."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 4000, 1000, 150000, 64, 3
+    d = synth.make_ratings(n, m, nnz, seed=41, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(42)
+    bounds = H.partition_users(d["row_ptr"], 2)
+    rp = d["row_ptr"].astype(np.int64)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("HPF_AR_OVERLAP", mode)  # read by hpf_comm_init
+        uid = H.comm_unique_id()
+        out, errs = [None, None], []
+
+        def worker(r):
+            try:
+                lo, hi = int(bounds[r]), int(bounds[r + 1])
+                with H.Engine(hi - lo, m, k, flags=flags, device=r, n_users_global=n) as e:
+                    e.comm_init(r, 2, uid)
+                    e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], d["y"][rp[lo]:rp[hi]])
+                    util.push_state(e, s, users=np.arange(lo, hi))
+                    e.iterate(iters)
+                    out[r] = {g: e.get_state(util._IDS[g]) for g in util.groups(s)}
+            except Exception as ex:  # surfaced in the main thread
+                errs.append(ex)
+
+        ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=600)
+        assert not errs, errs
+        runs[mode] = out
+    for r in range(2):
+        for g in util.groups(s):
+            for f in O.FIELDS:
+                np.testing.assert_array_equal(runs["0"][r][g][f], runs["1"][r][g][f], err_msg="rank %d %s.%s" % (r, g, f))
