@@ -191,3 +191,5 @@ def test_oracle_matches_live_reference_run():
     for gname in util.groups(want):
         for f in O.FIELDS:
             np.testing.assert_allclose(s.p[gname][f], want.p[gname][f], rtol=1e-12, atol=1e-13)
+    # and the reference's own logl() on that state (the harness calls it; printed with "%.5f")
+    assert abs(s.elbo(d0["csr.row_ptr"], d0["csr.col_idx"], d0["csr.y"]) - float(d2["elbo"][0])) <= util.TOL_ELBO_REF_PRINT
