@@ -190,6 +190,7 @@ struct hpf_ctx {
   TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
   DensePlan dense;               // the most popular items as a dense block on the tensor cores
   double dense_block_share = 0.06; // HPF_DENSE_BLOCK_SHARE: minimum share of the nonzeros for a 2nd..4th head block
+  int head_variant = 0;          // HPF_HEAD_VARIANT: experimental epilogues of head_kernel (hpf_head.cuh); 0 = the measured default
   int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 15 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
   uint32_t tile_rows = 0; size_t tile_smem = 0;
@@ -871,7 +872,10 @@ int launch_dense_head(hpf_ctx *c)
     c->launches++;
     d.a_dirty = false;
   }
-  CU(cudaFuncSetAttribute(head::head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
+  typedef void (*head_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const head::HeadArgs);
+  static const head_fn variants[4] = { head::head_kernel<0>, head::head_kernel<1>, head::head_kernel<2>, head::head_kernel<3> };
+  const head_fn kernel = variants[c->head_variant & 3];
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
   const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
   for (uint32_t b = 0; b < d.nblocks; ++b) { // one pass over the users per block of 128 head items
     const uint32_t nh = std::min<uint32_t>(head::kHead, d.nhead - b * head::kHead);
@@ -890,7 +894,7 @@ int launch_dense_head(hpf_ctx *c)
     a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
     a.Tb_theta = c->bias ? c->th.Tb : nullptr;
     a.ElogbT = c->th.b_Elog; a.ElogbB = c->be.b_Elog; a.TbdirectT = c->th.Tbdirect; a.TbdirectB = c->be.Tbdirect;
-    head::head_kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
+    kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
     head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T, c->bias ? c->be.Tb : nullptr);
     c->launches += 3;
   }
@@ -1064,6 +1068,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
     if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
     if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
+    if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 3;
     if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
       const uint32_t v = (uint32_t)atoi(e);
       if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }

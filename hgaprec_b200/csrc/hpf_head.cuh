@@ -111,6 +111,11 @@ __device__ __noinline__ void slow_pair(const HeadArgs &a, uint32_t u, uint32_t i
   *a.flagB = 1u;
 }
 
+// VARIANT (HPF_HEAD_VARIANT, experiments; 0 is the measured default and compiles to the code it always was):
+//   bit 0  epilogue 2 adds O to T_theta with red.global.add.v4.f32 instead of load + add + store (a row has one
+//          adder, so the result is the same and stays deterministic; no load round trip, half the traffic)
+//   bit 1  epilogue 1 fetches its 64 bytes of Y before waiting for Z (Y does not depend on the MMA)
+template <int VARIANT>
 __global__ void __launch_bounds__(kThreads, 1)
 head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const HeadArgs a)
@@ -216,14 +221,26 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const uint32_t u = tile * kUsers + r;
       const uint8_t *yrow = a.Y + (size_t)u * kHead;
       // ---- epilogue 1: P = y / Z, split into bf16 hi / lo, written K-major (items along the row) ----
+      uint4 yp0 = make_uint4(0u, 0u, 0u, 0u), yp1 = yp0, yp2 = yp0, yp3 = yp0;
+      if constexpr ((VARIANT & 2) != 0) {
+        const uint4 *yq = reinterpret_cast<const uint4 *>(yrow + half * 64u);
+        yp0 = __ldg(yq); yp1 = __ldg(yq + 1); yp2 = __ldg(yq + 2); yp3 = __ldg(yq + 3);
+      }
       mbar_wait(bar_z_full, ph);
       tc_fence_after();
 #pragma unroll 1
       for (uint32_t c = half * 2u; c < half * 2u + 2u; ++c) {
         uint32_t z[32];
         tc_ld32(tm_z + lane_addr + c * 32u, z);
-        const uint4 y0 = __ldg(reinterpret_cast<const uint4 *>(yrow + c * 32u));
-        const uint4 y1 = __ldg(reinterpret_cast<const uint4 *>(yrow + c * 32u + 16u));
+        uint4 y0, y1;
+        if constexpr ((VARIANT & 2) != 0) {
+          const bool first = c == half * 2u;
+          y0 = first ? yp0 : yp2;
+          y1 = first ? yp1 : yp3;
+        } else {
+          y0 = __ldg(reinterpret_cast<const uint4 *>(yrow + c * 32u));
+          y1 = __ldg(reinterpret_cast<const uint4 *>(yrow + c * 32u + 16u));
+        }
         const uint32_t yw[8] = { y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w };
         tc_wait_ld();
 #pragma unroll
@@ -272,7 +289,12 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           for (int j = 0; j < 32; j += 4) {
             const uint32_t k = c * 32u + j;
             if (k == a.K && a.Tb_theta != nullptr) a.Tb_theta[u] += __uint_as_float(o[j]); // the user-bias slot of phi
-            if (k < a.K) { // K is a multiple of 4 in storage (Kp): whole float4s, pad lanes are zero on both sides
+            if constexpr ((VARIANT & 1) != 0) {
+              if (k < a.K)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(trow + k), "f"(__uint_as_float(o[j])),
+                             "f"(__uint_as_float(o[j + 1])), "f"(__uint_as_float(o[j + 2])), "f"(__uint_as_float(o[j + 3]))
+                             : "memory");
+            } else if (k < a.K) { // K is a multiple of 4 in storage (Kp): whole float4s, pad lanes are zero on both sides
               float4 t = *reinterpret_cast<float4 *>(trow + k);
               t.x += __uint_as_float(o[j]); t.y += __uint_as_float(o[j + 1]);
               t.z += __uint_as_float(o[j + 2]); t.w += __uint_as_float(o[j + 3]);

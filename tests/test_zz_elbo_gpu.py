@@ -191,3 +191,31 @@ def test_two_gpu_elbo_parts_add_up(flags):
         t.join(timeout=600)
     assert not errs, errs
     assert abs(part[0] + part[1] - ref) <= TOL_ELBO_REL * abs(ref), (part, ref)
+
+
+# ------------------------------------------------------------------ experimental kernel variants (default off)
+@pytest.mark.skipif(os.environ.get("HPF_TEST_EXPERIMENTS") != "1",
+                    reason="HPF_HEAD_VARIANT epilogues are unmeasured experiments (default 0); set HPF_TEST_EXPERIMENTS=1")
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+@pytest.mark.parametrize("flags,k", [(H.HIER, 100), (H.HIER | H.BIAS, 64), (0, 5)])
+def test_head_kernel_variants_are_bitwise_the_default(monkeypatch, variant, flags, k):
+    """HPF_HEAD_VARIANT bit 0 (red.global.add.v4.f32 into T_theta: one adder per element) and bit 1 (Y fetched before
+    the wait on Z) change scheduling, not arithmetic: the state after three iterations must equal variant 0 bit for bit."""
+    monkeypatch.setenv("HPF_DENSE_HEAD", "1")
+    monkeypatch.setenv("HPF_DENSE_BLOCK_SHARE", "0")
+    d = synth.make_ratings(2100, 700, 90000, seed=61, heldout=0.05)
+    s = O.OracleState(d["n"], d["m"], k, flags).init(62)
+    out = {}
+    for v in ("0", variant):
+        monkeypatch.setenv("HPF_HEAD_VARIANT", v)
+        with _engine(s, extra=0) as e:
+            e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+            util.push_state(e, s)
+            e.iterate(3)
+            assert e.stats()["head_nnz"] > 0
+            out[v] = util.pull_state(e, s)
+    for gname in util.groups(s):
+        for f in O.FIELDS:
+            np.testing.assert_array_equal(out["0"].p[gname][f], out[variant].p[gname][f], err_msg="%s.%s" % (gname, f))
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], 3, nthreads=8)
+    assert not util.compare_states(out[variant], want, rel=6e-5, elog_abs=6e-5)
