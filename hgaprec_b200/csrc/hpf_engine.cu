@@ -873,8 +873,10 @@ int launch_dense_head(hpf_ctx *c)
     d.a_dirty = false;
   }
   typedef void (*head_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const head::HeadArgs);
-  static const head_fn variants[4] = { head::head_kernel<0>, head::head_kernel<1>, head::head_kernel<2>, head::head_kernel<3> };
-  const head_fn kernel = variants[c->head_variant & 3];
+  static const head_fn variants[8] = { head::head_kernel<0>, head::head_kernel<1>, head::head_kernel<2>, head::head_kernel<3>,
+                                       head::head_kernel<4>, head::head_kernel<5>, head::head_kernel<6>, head::head_kernel<7> };
+  const head_fn kernel = variants[c->head_variant & 7];
+  const int head_threads = head::head_threads(c->head_variant & 7);
   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
   const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
   for (uint32_t b = 0; b < d.nblocks; ++b) { // one pass over the users per block of 128 head items
@@ -894,7 +896,7 @@ int launch_dense_head(hpf_ctx *c)
     a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
     a.Tb_theta = c->bias ? c->th.Tb : nullptr;
     a.ElogbT = c->th.b_Elog; a.ElogbB = c->be.b_Elog; a.TbdirectT = c->th.Tbdirect; a.TbdirectB = c->be.Tbdirect;
-    kernel<<<grid, head::kThreads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
+    kernel<<<grid, head_threads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
     head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T, c->bias ? c->be.Tb : nullptr);
     c->launches += 3;
   }
@@ -1068,7 +1070,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
     if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
     if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
-    if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 3;
+    if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 7;
     if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
       const uint32_t v = (uint32_t)atoi(e);
       if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }

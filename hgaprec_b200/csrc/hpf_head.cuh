@@ -115,8 +115,14 @@ __device__ __noinline__ void slow_pair(const HeadArgs &a, uint32_t u, uint32_t i
 //   bit 0  epilogue 2 adds O to T_theta with red.global.add.v4.f32 instead of load + add + store (a row has one
 //          adder, so the result is the same and stays deterministic; no load round trip, half the traffic)
 //   bit 1  epilogue 1 fetches its 64 bytes of Y before waiting for Z (Y does not depend on the MMA)
+//   bit 2  the two epilogues get their own warps (2-9: epilogue 1, 10-17: epilogue 2; 576 threads): epilogue 2 of tile i
+//          runs under epilogue 1 and MMA 2/3 of tile i + 1.  One more barrier: "P free", committed with o_full, because
+//          epilogue 1 no longer follows epilogue 2 in program order.  The MMA thread's waits already order the rest
+//          (Z is rewritten only after p_full, O only after o_empty).
+constexpr int head_threads(int variant) { return (variant & 4) != 0 ? kThreads + 32 * kEpiWarps : kThreads; }
+
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(head_threads(VARIANT), 1)
 head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const HeadArgs a)
 {
@@ -125,13 +131,15 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_a_full = base + kSmemBar, bar_a_empty = bar_a_full + 8, bar_b_full = bar_a_full + 16,
                  bar_z_full = bar_a_full + 24, bar_p_full = bar_a_full + 32, bar_o_full = bar_a_full + 40,
-                 bar_o_empty = bar_a_full + 48;
+                 bar_o_empty = bar_a_full + 48, bar_p_free = bar_a_full + 56;
+  constexpr bool kSplit = (VARIANT & 4) != 0;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + kSmemBar + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     mbar_init(bar_a_full, 1); mbar_init(bar_a_empty, 1); mbar_init(bar_b_full, 1);
     mbar_init(bar_z_full, 1); mbar_init(bar_p_full, 32 * kEpiWarps); mbar_init(bar_o_full, 1); mbar_init(bar_o_empty, 32 * kEpiWarps);
+    if constexpr (kSplit) mbar_init(bar_p_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -208,12 +216,14 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         }
         tc_commit(bar_o_full);
         tc_commit(bar_a_empty);
+        if constexpr (kSplit) tc_commit(bar_p_free);
       }
     }
   } else {
     // ===== epilogue: two threads per user row (one per half of the columns) =====
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
-    const uint32_t half = (uint32_t)(warp - 2) >> 2;       // 0: columns 0-63, 1: columns 64-127
+    const bool do_ep1 = !kSplit || warp < 2 + kEpiWarps, do_ep2 = !kSplit || warp >= 2 + kEpiWarps;
+    const uint32_t half = (uint32_t)(kSplit && warp >= 2 + kEpiWarps ? warp - 2 - kEpiWarps : warp - 2) >> 2; // 0: columns 0-63, 1: 64-127
     const uint32_t r = (uint32_t)(q * 32 + lane);          // row inside the tile == TMEM lane
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -221,11 +231,13 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const uint32_t u = tile * kUsers + r;
       const uint8_t *yrow = a.Y + (size_t)u * kHead;
       // ---- epilogue 1: P = y / Z, split into bf16 hi / lo, written K-major (items along the row) ----
+      if (do_ep1) {
       uint4 yp0 = make_uint4(0u, 0u, 0u, 0u), yp1 = yp0, yp2 = yp0, yp3 = yp0;
       if constexpr ((VARIANT & 2) != 0) {
         const uint4 *yq = reinterpret_cast<const uint4 *>(yrow + half * 64u);
         yp0 = __ldg(yq); yp1 = __ldg(yq + 1); yp2 = __ldg(yq + 2); yp3 = __ldg(yq + 3);
       }
+      if constexpr (kSplit) mbar_wait(bar_p_free, ph ^ 1u); // MMA 2/3 of the previous tile has read P
       mbar_wait(bar_z_full, ph);
       tc_fence_after();
 #pragma unroll 1
@@ -275,7 +287,9 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes of P -> visible to the MMA
       tc_fence_before();
       mbar_arrive(bar_p_full);
+      }
       // ---- epilogue 2: T_theta[u] += O[u] ----
+      if (do_ep2) {
       mbar_wait(bar_o_full, ph);
       tc_fence_after();
       float *trow = a.T_theta + (size_t)u * a.ld;
@@ -305,9 +319,10 @@ head_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(bar_o_empty);
+      }
     }
     // ---- after the last tile: this CTA's dB (head items x factors), one thread per head item ----
-    {
+    if (do_ep2) {
       float *brow = a.dB_part + ((size_t)blockIdx.x * kHead + r) * kFact;
 #pragma unroll 1
       for (uint32_t c = half * 2u; c < half * 2u + 2u; ++c) {
