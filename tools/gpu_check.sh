@@ -13,7 +13,7 @@ fi
 timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-  KREGEX='regex:sweep_kernel|update_kernel|combine_kernel|colsum|heldout|topn|head_kernel|head_reduce|split_kernel'
+  KREGEX='regex:sweep_kernel|update_kernel|combine_kernel|colsum|heldout|topn|head_kernel|head_reduce|split_kernel|split_aux_kernel|nnz_kernel|gamma_'
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 400 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 \
       > gpurun_out/bench_under_ncu.log 2>&1
