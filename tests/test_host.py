@@ -154,3 +154,57 @@ def test_csr_cache_in_a_read_only_directory_is_not_an_error(hostcheck, tmp_path)
             assert "csr cache: not written" in out
     finally:
         os.chmod(data, 0o755)
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference/src") and os.path.exists(O.REF_HARNESS)),
+                    reason="needs /root/reference and the oracle/_ref build")
+def test_reader_matches_the_live_reference_on_random_files(hostcheck, tmp_path):
+    """Differential test against the unmodified reference reader (Ratings::read_generic, src/ratings.cc:63-119, behind
+    oracle/_ref/ref_harness): random files with repeated lines, zero ratings, values past uint8, -n / -m below and above
+    what the file holds (the reference shrinks both to what it read, so held-out lines never add users or items),
+    held-out lines naming unseen users / items, -binary-data with random thresholds."""
+    for seed in range(30):
+        rng = np.random.default_rng(seed)
+        nu, ni = int(rng.integers(4, 25)), int(rng.integers(4, 25))
+        uids = rng.choice(np.arange(100, 400), nu, replace=False)
+        iids = rng.choice(np.arange(1000, 1400), ni, replace=False)
+
+        def lines(cnt, strangers):
+            out = []
+            for _ in range(cnt):
+                u, i = int(rng.choice(uids)), int(rng.choice(iids))
+                if strangers and rng.random() < 0.2:
+                    i = int(rng.integers(2000, 2010))
+                if strangers and rng.random() < 0.1:
+                    u = int(rng.integers(500, 505))
+                out.append("%d\t%d\t%d" % (u, i, int(rng.choice([0, 1, 2, 3, 4, 5, 5, 255, 256, 260, 300]))))
+            return out
+
+        train = lines(int(rng.integers(30, 200)), False)
+        if rng.random() < 0.5:
+            train.sort(key=lambda s: int(s.split("\t")[0]))  # grouped by user, as real files are
+        binary, thr = bool(rng.random() < 0.4), int(rng.integers(1, 5))
+        seen_u, seen_i = len({l.split("\t")[0] for l in train}), len({l.split("\t")[1] for l in train})
+        n_cap = max(1, seen_u - int(rng.integers(0, 3)))
+        m_cap = max(1, seen_i - int(rng.integers(0, 3))) + (3 if seed % 2 else 0)
+        run = tmp_path / ("c%d" % seed)
+        data = str(run / "data")
+        os.makedirs(data)
+        open(os.path.join(data, "train.tsv"), "w").write("\n".join(train) + "\n")
+        open(os.path.join(data, "validation.tsv"), "w").write("\n".join(lines(20, True)) + "\n")
+        open(os.path.join(data, "test.tsv"), "w").write("\n".join(lines(40, True)) + "\n")
+        O.run_ref_harness(data, n_cap, m_cap, 3, [0], str(run / "r"), str(run), hier=True, binary=binary,
+                          rating_threshold=thr, seed=3)
+        ref = O.read_dump(str(run / "r_0.bin"))
+        args = [hostcheck, "-dir", data, "-n", str(n_cap), "-m", str(m_cap), "-k", "3", "-hier", "-seed", "3",
+                "-rating-threshold", str(thr), "-out", str(run / "h.bin")] + (["-binary-data"] if binary else [])
+        subprocess.check_call(args)
+        got = O.read_dump(str(run / "h.bin"))
+        for key in ("csr.row_ptr", "csr.col_idx", "seq2user", "seq2movie", "validation.u", "validation.i", "validation.y",
+                    "test.u", "test.i", "test.y"):
+            np.testing.assert_array_equal(got[key], ref[key], err_msg="seed %d %s" % (seed, key))
+        if not binary:  # a rating that wrapped to 0 in the uint8 is walked as 1 (the loop only scales y > 1)
+            np.testing.assert_array_equal(got["csr.y"], np.where(ref["csr.y"] == 0, 1, ref["csr.y"]), err_msg="seed %d y" % seed)
+        # same model dimensions and the same start state (same number of generator draws)
+        np.testing.assert_allclose(got["htheta.shape"], ref["htheta.shape"], rtol=1e-14, err_msg="seed %d" % seed)
+        np.testing.assert_allclose(got["hbeta.Ev"], ref["hbeta.Ev"], rtol=1e-13, err_msg="seed %d" % seed)
