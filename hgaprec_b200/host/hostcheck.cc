@@ -25,7 +25,7 @@ static void put(FILE *f, const char *name, uint32_t dtype, const void *data, siz
   fwrite(&nd, 4, 1, f);
   size_t cnt = 1;
   for (size_t i = 0; i < dims.size(); ++i) { fwrite(&dims[i], 8, 1, f); cnt *= dims[i]; }
-  fwrite(data, itemsize, cnt, f);
+  if (cnt) fwrite(data, itemsize, cnt, f);
 }
 static void put_f64(FILE *f, const std::string &name, const std::vector<double> &v, uint64_t rows, uint64_t cols)
 {
