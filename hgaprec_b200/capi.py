@@ -45,8 +45,9 @@ class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("iterations", ctypes.c_uint64),
                 ("slow_path_nnz", ctypes.c_uint64), ("nnz", ctypes.c_uint64), ("device_bytes", ctypes.c_uint64),
                 ("last_iterate_ms", ctypes.c_float), ("sweep_group", ctypes.c_uint32), ("sweep_vec", ctypes.c_uint32),
-                ("tile_rows", ctypes.c_uint32), ("item_tiles", ctypes.c_uint32), ("head_nnz", ctypes.c_uint64),
-                ("tile_segments", ctypes.c_uint64), ("last_topn_ms", ctypes.c_float)]
+                ("user_l2_tiles", ctypes.c_uint32), ("item_l2_tiles", ctypes.c_uint32), ("head_nnz", ctypes.c_uint64),
+                ("item_chunks", ctypes.c_uint32), ("mg_exact", ctypes.c_uint32), ("last_topn_ms", ctypes.c_float),
+                ("n_devices", ctypes.c_uint32)]
 
 
 class IterProfile(ctypes.Structure):

@@ -109,18 +109,6 @@ struct Arena {
   }
 };
 
-struct TilePlan {       // work of one tile_sweep_kernel launch
-  bool on = false;
-  uint4 *seg = nullptr; size_t seg_cap = 0;
-  uint32_t *tile_ptr = nullptr; size_t tile_ptr_cap = 0;
-  uint32_t *idx = nullptr; size_t idx_cap = 0;   // per nonzero: slot inside its tile
-  uint8_t *y = nullptr; size_t y_cap = 0;
-  uint32_t *row_ids = nullptr; size_t row_ids_cap = 0; // explicit rows of a single tile (head items)
-  uint32_t ntiles = 0, cpt = 1, nsegs = 0, tile0_count = 0;
-  uint64_t nnz = 0;
-  bool has_y = false;
-};
-
 struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
   bool on = false;
   uint32_t *Yw = nullptr; size_t Yw_cap = 0;          // dense head ratings, as 32-bit words
@@ -136,7 +124,8 @@ struct DensePlan {      // dense head of the sweep on tcgen05 (hpf_head.cuh)
 constexpr uint32_t kMaxHeadBlocks = 4;
 constexpr uint32_t kElboLaunches = 7; // nnz, theta, beta, xi, eta, theta bias, beta bias
 
-struct WorkList {       // segments of one orientation, sorted by descending length
+constexpr uint32_t kMaxChunks = 16;
+struct WorkList {       // segments of one orientation: (chunk of rows, L2 tile, descending length)
   uint4 *seg = nullptr;
   uint32_t *seg_out = nullptr;
   uint32_t nsegs = 0, npartial = 0, nmulti = 0;
@@ -144,6 +133,9 @@ struct WorkList {       // segments of one orientation, sorted by descending len
   const uint32_t *idx = nullptr; // device, per nonzero
   const uint8_t *y = nullptr;
   size_t seg_cap = 0, seg_out_cap = 0, multi_cap[3] = { 0, 0, 0 };
+  // chunks of rows, launched one after the other (all-reduce of chunk c under the sweep of chunk c + 1)
+  uint32_t nchunks = 1, chunk_rows = 0;
+  uint32_t chunk_seg[kMaxChunks + 1] = { 0 }, chunk_multi[kMaxChunks + 1] = { 0 };
 };
 
 struct Side {
@@ -157,6 +149,10 @@ struct Side {
   float2 *aux = nullptr;
   float *colsum = nullptr;         // [Kp] sum over rows of Ev (this side)
   float *colsum_partial = nullptr; // [update_grid x Kp]
+  // the two terms of the rate the last update used: rate_uk = rate_row[u] + rate_col[k] (hier), or the GR
+  // rate vector in rate_col.  Ev / rate are materialised from them on demand (derived_valid).
+  float *rate_row = nullptr, *rate_col = nullptr;
+  bool derived_valid = false;
   uint32_t *direct_flag = nullptr;
   uint32_t update_grid = 0;
   size_t tpart_cap = 0, tbpart_cap = 0;
@@ -175,7 +171,7 @@ struct hpf_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t pev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t pev[16] = { nullptr };
   bool profiling = false;
   std::string err;
   std::vector<std::pair<void *, size_t>> allocs;
@@ -186,15 +182,12 @@ struct hpf_ctx {
   uint32_t *csr_idx = nullptr, *csc_idx = nullptr, *upass_idx = nullptr; // upass_*: CSR regrouped by item tile (or null)
   uint8_t *csr_y = nullptr, *csc_y = nullptr, *upass_y = nullptr;
   size_t csr_idx_cap = 0, csr_y_cap = 0, csc_idx_cap = 0, csc_y_cap = 0, upass_idx_cap = 0, upass_y_cap = 0;
-  Arena dev_arena, dev_arena2, pin_arena; // grow-only device / pinned-host scratch of hpf_set_ratings_csr
-  TilePlan item_tile, head_tile; // shared-memory tile sweeps: item pass over user blocks, user-pass head items
+  Arena dev_arena, pin_arena;    // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   DensePlan dense;               // the most popular items as a dense block on the tensor cores
   double dense_block_share = 0.06; // HPF_DENSE_BLOCK_SHARE: minimum share of the nonzeros for a 2nd..4th head block
-  int head_variant = 0;          // HPF_HEAD_VARIANT: experimental epilogues of head_kernel (hpf_head.cuh); 0 = the measured default
+  int head_variant = 7;          // HPF_HEAD_VARIANT: epilogue organisation of head_kernel (hpf_head.cuh); 7 measured fastest (profiles/r02b_exp_head_variants.log)
   int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 15 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
-  uint32_t tile_rows = 0; size_t tile_smem = 0;
-  int item_tile_mode = 0, head_tile_mode = 0; // 0 off (default: measured slower than the gather kernel), 1 forced, -1 auto
   uint32_t th_tiles = 1, be_tiles = 1;
   uint64_t l2_tile_bytes = 32ull << 20; // factor rows of one gather tile (0: no tiling)
   bool l2_tile_forced = false;          // HPF_L2_TILE_KB (tests): ignore the run-length cap
@@ -202,9 +195,11 @@ struct hpf_ctx {
   uint32_t seg_len = 512;
   int sweep_g = 0, sweep_v = 0;
   bool aux_dirty = true, ratings_set = false, th_colsum_global = false;
-  // item-side reduce block [T_beta | Tb_beta | colsum_theta] (one allreduce)
-  float *redblock = nullptr;
-  size_t red_count = 0;
+  // item-side reduce block [T_beta | Tb_beta | colsum_theta | fallback flag]: T_beta is all-reduced chunk by
+  // chunk, the tail [Tb_beta | colsum_theta | flag] in one piece; redblock2 = [Tdirect_beta | Tbdirect_beta]
+  float *redblock = nullptr, *red_tail = nullptr, *red_flag = nullptr, *redblock2 = nullptr;
+  size_t red_count = 0, red_tail_count = 0, red2_count = 0;
+  float *mg_fired = nullptr;         // device: sum of the all-reduced fallback flags since it was last cleared
   float *colsum_theta_old = nullptr; // -novb
   unsigned long long *slow_count = nullptr;
   double *logfact = nullptr, *ll_blocks = nullptr, *ll_out = nullptr;
@@ -212,13 +207,19 @@ struct hpf_ctx {
   bool logl = false, pr_prev_valid = false, csr_has_y = false;
   uint64_t *csr_rowptr = nullptr; size_t csr_rowptr_cap = 0; // device copy of the CSR row pointer
   double *elbo_blocks = nullptr;                             // [kElboLaunches x sm_count x 8] per-block partial sums
-  // multi-GPU
+  // multi-GPU: every collective of this ctx is issued on comm_stream, in the same order on all ranks; events
+  // carry the dependencies to and from the compute stream (one_iteration)
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  // HPF_AR_OVERLAP=1 (opt-in): the all-reduce of [T_beta | Tb_beta] runs on its own stream under the theta update
-  bool ar_overlap = false;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_tbeta = nullptr, ev_ar = nullptr;
+  cudaEvent_t ev_chunk[kMaxChunks] = { nullptr }, ev_theta = nullptr, ev_comm = nullptr;
+  int ar_chunks = -1;             // HPF_AR_CHUNKS: chunks of the item pass (-1: from the payload size)
+  // A nonzero that takes the exact fallback adds to the rank-local Tdirect buffers; on the item side those would
+  // have to be summed over the ranks too.  That never happens in a real fit, so the reduction is
+  // optimistic: the ranks agree on a "fallback fired" flag that rides with the column sums, and hpf_iterate re-runs
+  // its window from a snapshot with the fallback buffers inside the all-reduce (mg_exact, sticky) when it is set.
+  bool mg_exact = false;
+  float *snap = nullptr; size_t snap_cap = 0;
   // stats
   uint64_t launches = 0, iterations = 0;
   float last_ms = 0.f, last_topn_ms = 0.f;
@@ -284,6 +285,30 @@ uint32_t row_grid(const hpf_ctx *c, uint32_t R)
   return std::max(1u, std::min(need, cap));
 }
 
+// grid of update_kernel: one resident wave (the kernel strides over the rows and keeps column sums in registers)
+template <int V> int update_occupancy()
+{
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, update_kernel<V>, kUpdateWarps * 32, 0) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+uint32_t update_grid_for(const hpf_ctx *c, uint32_t R)
+{
+  int occ = 1;
+  switch ((c->K4 + 31) / 32) {
+  case 1: occ = update_occupancy<1>(); break;
+  case 2: occ = update_occupancy<2>(); break;
+  case 3: occ = update_occupancy<3>(); break;
+  case 4: occ = update_occupancy<4>(); break;
+  case 5: occ = update_occupancy<5>(); break;
+  case 6: occ = update_occupancy<6>(); break;
+  case 7: occ = update_occupancy<7>(); break;
+  default: occ = update_occupancy<8>(); break;
+  }
+  const uint32_t need = (R + kUpdateWarps - 1) / kUpdateWarps;
+  return std::max(1u, std::min(need, (uint32_t)c->sm_count * (uint32_t)occ));
+}
+
 // pick lanes-per-nonzero G and float4-per-lane V: smallest G with V <= 4 (measured best at K=100:
 // G=8/V=4 beats G=4/V=7 -- fewer registers, twice the resident warps)
 void pick_sweep_shape(hpf_ctx *c)
@@ -299,7 +324,8 @@ void pick_sweep_shape(hpf_ctx *c)
   c->sweep_v = (int)((c->K4 + g - 1) / g);
 }
 
-int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
+// own_direct: the side allocates its fallback buffers itself (the item side's live in the second reduce block)
+int alloc_side(hpf_ctx *c, Side &s, uint32_t R, bool own_direct)
 {
   s.R = R;
   const size_t rk = (size_t)R * c->ld;
@@ -308,7 +334,9 @@ int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
   TRY(dalloc(c, &s.Ev, rk));
   TRY(dalloc(c, &s.shape, rk));
   TRY(dalloc(c, &s.rate, c->hier ? rk : (size_t)c->Kp));
-  TRY(dalloc(c, &s.Tdirect, rk));
+  TRY(dalloc(c, &s.rate_col, c->Kp));
+  if (c->hier) TRY(dalloc(c, &s.rate_row, R));
+  if (own_direct) TRY(dalloc(c, &s.Tdirect, rk));
   TRY(dalloc(c, &s.shift, R));
   TRY(dalloc(c, &s.direct_flag, 1));
   if (c->hier) {
@@ -325,18 +353,18 @@ int alloc_side(hpf_ctx *c, Side &s, uint32_t R)
     TRY(dalloc(c, &s.b_rate, R));
     TRY(dalloc(c, &s.b_Ev, R));
     TRY(dalloc(c, &s.b_Elog, R));
-    TRY(dalloc(c, &s.Tbdirect, R));
+    if (own_direct) TRY(dalloc(c, &s.Tbdirect, R));
     TRY(dalloc(c, &s.aux, R));
   }
-  s.update_grid = row_grid(c, R);
-  TRY(dalloc(c, &s.colsum_partial, (size_t)s.update_grid * c->Kp));
+  s.update_grid = update_grid_for(c, R);
+  TRY(dalloc(c, &s.colsum_partial, (size_t)std::max(s.update_grid, row_grid(c, R)) * c->Kp));
   return 0;
 }
 
 // ---- sweep dispatch ----------------------------------------------------------
 template <int G, int V> int launch_sweep_gv(hpf_ctx *c, const SweepArgs &a)
 {
-  const uint32_t groups_per_block = kSweepThreads / G;
+  constexpr uint32_t groups_per_block = kSweepThreads / G;
   const uint32_t grid = (a.nsegs + groups_per_block - 1) / groups_per_block;
   if (grid == 0) return 0;
   if (c->bias) sweep_kernel<G, V, true><<<grid, kSweepThreads, 0, c->stream>>>(a);
@@ -361,12 +389,14 @@ template <int G> int launch_sweep_g(hpf_ctx *c, const SweepArgs &a)
   return fail(c, HPF_EINVAL, "unsupported sweep shape G=%d V=%d", G, c->sweep_v);
 }
 
-int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside)
+// sweep over the segments of chunk `chunk` of the row side's work list (chunk < 0: all of them)
+int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside, int chunk = -1)
 {
   SweepArgs a;
   memset(&a, 0, sizeof a);
   const WorkList &w = rowside.wl;
-  a.seg = w.seg; a.seg_out = w.seg_out; a.nsegs = w.nsegs; a.R = rowside.R;
+  const uint32_t s0 = chunk < 0 ? 0u : w.chunk_seg[chunk], s1 = chunk < 0 ? w.nsegs : w.chunk_seg[chunk + 1];
+  a.seg = w.seg + s0; a.seg_out = w.seg_out + s0; a.nsegs = s1 - s0; a.R = rowside.R;
   a.idx = w.idx; a.y = w.y;
   a.Arow = rowside.A; a.Acol = colside.A;
   a.T = rowside.T; a.Tpart = rowside.Tpart;
@@ -388,84 +418,45 @@ int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside)
   return fail(c, HPF_EINVAL, "unsupported sweep group %d", c->sweep_g);
 }
 
-template <int G, int V> int launch_tile_gv(hpf_ctx *c, const TileArgs &a, uint32_t grid)
+int launch_combine(hpf_ctx *c, Side &s, int chunk = -1)
 {
-  if (c->bias) {
-    CU(cudaFuncSetAttribute(tile_sweep_kernel<G, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-    tile_sweep_kernel<G, V, true><<<grid, kTileThreads, c->tile_smem, c->stream>>>(a);
-  } else {
-    CU(cudaFuncSetAttribute(tile_sweep_kernel<G, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-    tile_sweep_kernel<G, V, false><<<grid, kTileThreads, c->tile_smem, c->stream>>>(a);
-  }
-  c->launches++;
-  CU(cudaGetLastError());
-  return 0;
-}
-
-template <int G> int launch_tile_g(hpf_ctx *c, const TileArgs &a, uint32_t grid)
-{
-  switch (c->sweep_v) {
-  case 1: return launch_tile_gv<G, 1>(c, a, grid);
-  case 2: return launch_tile_gv<G, 2>(c, a, grid);
-  case 3: return launch_tile_gv<G, 3>(c, a, grid);
-  case 4: return launch_tile_gv<G, 4>(c, a, grid);
-  case 5: return launch_tile_gv<G, 5>(c, a, grid);
-  case 6: return launch_tile_gv<G, 6>(c, a, grid);
-  case 7: return launch_tile_gv<G, 7>(c, a, grid);
-  case 8: return launch_tile_gv<G, 8>(c, a, grid);
-  }
-  return fail(c, HPF_EINVAL, "unsupported sweep shape G=%d V=%d", G, c->sweep_v);
-}
-
-// tile sweep of `plan`: rows on `rowside`, tiles of `colside` rows staged in shared memory; adds into rowside.T
-int launch_tile_sweep(hpf_ctx *c, const TilePlan &plan, Side &rowside, Side &colside)
-{
-  if (!plan.on || plan.nsegs == 0) return 0;
-  TileArgs a;
-  memset(&a, 0, sizeof a);
-  a.seg = plan.seg; a.tile_seg_ptr = plan.tile_ptr; a.ntiles = plan.ntiles; a.cpt = plan.cpt;
-  a.tile_rows = c->tile_rows; a.C = colside.R;
-  a.tile_row_ids = plan.tile0_count ? plan.row_ids : nullptr; a.tile0_count = plan.tile0_count;
-  a.idx = plan.idx; a.y = plan.has_y ? plan.y : nullptr;
-  a.Arow = rowside.A; a.Acol = colside.A; a.T = rowside.T;
-  a.row_aux = rowside.aux; a.col_aux = colside.aux; a.Tb = rowside.Tb;
-  a.ElogRow = rowside.Elog; a.ElogCol = colside.Elog; a.ElogbRow = rowside.b_Elog; a.ElogbCol = colside.b_Elog;
-  a.Tdirect = rowside.Tdirect; a.Tbdirect = rowside.Tbdirect; a.direct_flag = rowside.direct_flag; a.slow_count = c->slow_count;
-  a.K = c->K; a.K4 = c->K4; a.ld = c->ld; a.ld4 = c->ld / 4;
-  const uint32_t grid = std::min<uint32_t>(plan.ntiles * plan.cpt, (uint32_t)c->sm_count);
-  switch (c->sweep_g) {
-  case 1: return launch_tile_g<1>(c, a, grid);
-  case 2: return launch_tile_g<2>(c, a, grid);
-  case 4: return launch_tile_g<4>(c, a, grid);
-  case 8: return launch_tile_g<8>(c, a, grid);
-  case 16: return launch_tile_g<16>(c, a, grid);
-  case 32: return launch_tile_g<32>(c, a, grid);
-  }
-  return fail(c, HPF_EINVAL, "unsupported sweep group %d", c->sweep_g);
-}
-
-int launch_combine(hpf_ctx *c, Side &s)
-{
-  if (s.wl.nmulti == 0) return 0;
+  const uint32_t m0 = chunk < 0 ? 0u : s.wl.chunk_multi[chunk], m1 = chunk < 0 ? s.wl.nmulti : s.wl.chunk_multi[chunk + 1];
+  if (m1 == m0) return 0;
   CombineArgs a;
-  a.multi_row = s.wl.multi_row; a.multi_first = s.wl.multi_first; a.multi_cnt = s.wl.multi_cnt;
-  a.nmulti = s.wl.nmulti; a.Kp = c->Kp; a.ld = c->ld; a.Tpart = s.Tpart; a.T = s.T;
+  a.multi_row = s.wl.multi_row + m0; a.multi_first = s.wl.multi_first + m0; a.multi_cnt = s.wl.multi_cnt + m0;
+  a.nmulti = m1 - m0; a.Kp = c->Kp; a.ld = c->ld; a.Tpart = s.Tpart; a.T = s.T;
   a.Tbpart = c->bias ? s.Tbpart : nullptr; a.Tb = s.Tb;
   const size_t sm = ((size_t)kUpdateWarps * c->Kp + kUpdateWarps) * sizeof(float);
-  combine_kernel<<<s.wl.nmulti, kUpdateWarps * 32, sm, c->stream>>>(a);
+  combine_kernel<<<m1 - m0, kUpdateWarps * 32, sm, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
 }
 
+template <int V> int launch_update_v(hpf_ctx *c, const UpdateArgs &a, uint32_t grid)
+{
+  const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
+  update_kernel<V><<<grid, kUpdateWarps * 32, sm, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// dense update of one side.  colsum_other: the other side's column sums of E[v]; bias_count: what the bias rate adds
+// (m for users, n_global for items).  The theta update also publishes the item side's fallback flag next to its
+// column sums (tail of the reduce block); the beta update accumulates the all-reduced flag (multi-GPU).
 int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_count)
 {
+  const bool theta = &s == &c->th;
   UpdateArgs a;
   memset(&a, 0, sizeof a);
-  a.R = s.R; a.K = c->K; a.Kp = c->Kp; a.ld = c->ld;
-  a.T = s.T; a.Tdirect = s.Tdirect; a.direct_flag = s.direct_flag;
-  a.A = s.A; a.Elog = s.Elog; a.Ev = s.Ev; a.shape = s.shape; a.rate = s.rate; a.shift = s.shift;
+  a.R = s.R; a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4; a.ld4 = c->ld / 4;
+  a.T = reinterpret_cast<const float4 *>(s.T); a.Tdirect = reinterpret_cast<float4 *>(s.Tdirect); a.direct_flag = s.direct_flag;
+  a.direct_flag_all = (!theta && c->mg_exact && c->nranks > 1) ? c->red_flag : nullptr;
+  a.A = reinterpret_cast<float4 *>(s.A); a.Elog = reinterpret_cast<float4 *>(s.Elog); a.shape = reinterpret_cast<float4 *>(s.shape);
+  a.shift = s.shift;
   a.hier = c->hier; a.colsum_other = colsum_other;
+  a.rate_vec = s.rate_col; a.rate_row = s.rate_row;
   a.prior_shape = (float)s.prior_shape; a.prior_rate = (float)s.prior_rate;
   a.pr_shape = s.pr_shape; a.pr_rate = s.pr_rate; a.pr_Ev = s.pr_Ev;
   a.pr_prior_shape = (float)s.pr_prior_shape; a.pr_prior_rate = (float)s.pr_prior_rate;
@@ -474,17 +465,50 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   a.bias_prior_shape = (float)s.bias_prior_shape;
   a.bias_rate_total = (float)(s.bias_prior_rate + bias_count);
   a.colsum_partial = s.colsum_partial;
-  if (&s == &c->th && c->dense.on && !c->dense.a_dirty) { // keep the dense head's operand copy of A in step
+  if (theta && c->dense.on && !c->dense.a_dirty) { // keep the dense head's operand copy of A in step
     a.split_hi = c->dense.a_hi; a.split_lo = c->dense.a_lo; a.split_ld = head::kFact;
   }
-  const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
-  update_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(a);
+  // hier: the column term of the rate this update uses, kept for derive_kernel (the GR vector is written by the kernel)
+  if (c->hier) CU(cudaMemcpyAsync(s.rate_col, colsum_other, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
+  s.derived_valid = false;
+  switch ((c->K4 + 31) / 32) {
+  case 1: TRY(launch_update_v<1>(c, a, s.update_grid)); break;
+  case 2: TRY(launch_update_v<2>(c, a, s.update_grid)); break;
+  case 3: TRY(launch_update_v<3>(c, a, s.update_grid)); break;
+  case 4: TRY(launch_update_v<4>(c, a, s.update_grid)); break;
+  case 5: TRY(launch_update_v<5>(c, a, s.update_grid)); break;
+  case 6: TRY(launch_update_v<6>(c, a, s.update_grid)); break;
+  case 7: TRY(launch_update_v<7>(c, a, s.update_grid)); break;
+  case 8: TRY(launch_update_v<8>(c, a, s.update_grid)); break;
+  default: return fail(c, HPF_EINVAL, "unsupported factor count %u", c->K);
+  }
+  const bool mg = c->nranks > 1;
+  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(
+      s.colsum_partial, s.update_grid, c->Kp, s.colsum, s.direct_flag,
+      theta && mg ? c->be.direct_flag : nullptr, theta && mg ? c->red_flag : nullptr,
+      !theta && mg ? c->red_flag : nullptr, !theta && mg ? c->mg_fired : nullptr);
   c->launches++;
   CU(cudaGetLastError());
-  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
-                                                                     s.direct_flag);
+  return 0;
+}
+
+// E[v] and the rate matrix of a side, materialised from shape and the rate terms of the last update
+// (report-window consumers: held-out ll, top-N, ELBO, hpf_get_state)
+int ensure_derived(hpf_ctx *c, Side &s)
+{
+  if (s.derived_valid) return 0;
+  DeriveArgs a;
+  a.R = s.R; a.K = c->K; a.K4 = c->K4; a.ld4 = c->ld / 4;
+  a.shape = reinterpret_cast<const float4 *>(s.shape); a.Ev = reinterpret_cast<float4 *>(s.Ev);
+  a.rate = c->hier ? reinterpret_cast<float4 *>(s.rate) : nullptr;
+  a.hier = c->hier; a.rate_row = s.rate_row; a.rate_col = s.rate_col;
+  const uint64_t total = (uint64_t)s.R * c->K4;
+  const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16));
+  derive_kernel<<<grid, 256, 0, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
+  if (!c->hier) CU(cudaMemcpyAsync(s.rate, s.rate_col, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
+  s.derived_valid = true;
   return 0;
 }
 
@@ -495,7 +519,7 @@ int refresh_colsum(hpf_ctx *c, Side &s)
   c->launches++;
   CU(cudaGetLastError());
   colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
-                                                                     nullptr);
+                                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -570,178 +594,123 @@ struct Scratch {
   }
 };
 
-// ---- work lists ---------------------------------------------------------------
-// The nonzeros of one orientation arrive as RUNS: run (t, r) holds the nonzeros
-// of row r whose gathered-side index lies in tile t, ptr[t * R + r] is where it
-// starts (ntiles == 1: ptr is the plain CSR row pointer).  Every run is split
-// into segments of <= seg_len nonzeros.  A row with one segment writes its T row
-// directly; a row with several writes partial slots that combine_kernel adds in
-// a fixed order.  Segments are emitted tile by tile -- blocks are scheduled in
-// index order, so at any moment the gathers fall into one tile's L2-resident
-// factor rows -- and, inside a tile, counting-sorted by descending length so
-// that (a) the 32/G segments a warp advances in lock-step have equal trip counts
-// and (b) long work is scheduled first.
-struct HostWorkList { // lives in the pinned host arena until uploaded
-  uint4 *seg = nullptr;
-  uint32_t *seg_out = nullptr, *multi_row = nullptr, *multi_first = nullptr, *multi_cnt = nullptr;
-  uint32_t nsegs = 0, nslots = 0, nmulti = 0;
+// ---- work lists, built on the device (kernels and the ordering: hpf_kernels.cuh, "work lists") -------------
+// Everything is enqueued on the ctx stream; the counts (segments, partial slots, multi-segment rows, chunk
+// boundaries) land in pinned memory and are read by finish_worklist after the caller's next synchronisation.
+struct WlPending {
+  uint32_t *h_info = nullptr; // pinned {nsegs, nslots, nmulti, 0, seg bound[nchunks + 1], multi bound[nchunks + 1]}
+  uint32_t nchunks = 1, chunk_rows = 0;
 };
 
-// upper bound of the pinned bytes build_worklist_host carves for one orientation
-size_t worklist_host_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L)
+uint64_t worklist_seg_bound(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L)
 {
-  const uint64_t segs = nnz / L + (uint64_t)ntiles * R + R + 16;
-  return pad256(segs * sizeof(uint4)) + pad256(segs * 4) + 3 * pad256((size_t)R * 4) + 4096;
+  return nnz / L + std::min<uint64_t>(nnz, (uint64_t)ntiles * R) + R + 1;
 }
 
-// skip (optional, R flags): rows that get NO segment at all, not even the empty one that clears T --
-// the head items of the dense-head plan, whose T rows belong to head_kernel.
-int build_worklist_host(hpf_ctx *c, Arena &pin, uint32_t R, const uint64_t *ptr, uint32_t ntiles, HostWorkList *out,
-                        const std::vector<uint8_t> *skip = nullptr)
+size_t worklist_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L, size_t cub_bytes)
 {
-  const uint32_t L = c->seg_len;
-  auto skipped = [&](uint32_t r) { return skip != nullptr && (*skip)[r] != 0; };
-  std::vector<uint32_t> segcnt(R, 0);
-  for (uint32_t t = 0; t < ntiles; ++t) {
-    const uint64_t *pt = ptr + (size_t)t * R;
-    for (uint32_t r = 0; r < R; ++r) {
-      const uint64_t len = pt[r + 1] - pt[r];
-      if (len && !skipped(r)) segcnt[r] += (uint32_t)((len + L - 1) / L);
-    }
-  }
-  uint64_t nsegs64 = 0;
-  uint32_t nmulti = 0;
-  for (uint32_t r = 0; r < R; ++r) {
-    if (skipped(r)) continue;
-    nsegs64 += segcnt[r] ? segcnt[r] : 1;
-    nmulti += segcnt[r] > 1;
-  }
-  if (nsegs64 >= 0xfffffff0ull) return fail(c, HPF_EINVAL, "too many work segments (%llu)", (unsigned long long)nsegs64);
-  const uint32_t nsegs = (uint32_t)nsegs64;
-  HostWorkList w;
-  w.seg = pin.get<uint4>(nsegs);
-  w.seg_out = pin.get<uint32_t>(nsegs);
-  w.multi_row = pin.get<uint32_t>(nmulti);
-  w.multi_first = pin.get<uint32_t>(nmulti);
-  w.multi_cnt = pin.get<uint32_t>(nmulti);
-  if (!w.seg || !w.seg_out || !w.multi_row || !w.multi_first || !w.multi_cnt)
-    return fail(c, HPF_ENOMEM, "pinned work-list arena too small");
-  std::vector<uint32_t> first(R, 0), next(R, 0);
-  uint32_t nslots = 0, mi = 0;
-  for (uint32_t r = 0; r < R; ++r)
-    if (segcnt[r] > 1) {
-      w.multi_row[mi] = r; w.multi_first[mi] = nslots; w.multi_cnt[mi] = segcnt[r];
-      ++mi;
-      first[r] = nslots;
-      nslots += segcnt[r];
-    }
-  std::vector<uint32_t> bucket(L + 2);
-  uint32_t base = 0;
-  for (uint32_t t = 0; t < ntiles; ++t) {
-    const uint64_t *pt = ptr + (size_t)t * R;
-    // counting sort by length, descending: bucket b holds length L - b
-    std::fill(bucket.begin(), bucket.end(), 0u);
-    for (uint32_t r = 0; r < R; ++r) {
-      if (skipped(r)) continue;
-      const uint64_t len = pt[r + 1] - pt[r];
-      if (len == 0) {
-        if (t == 0 && segcnt[r] == 0) bucket[L + 1]++; // a row without nonzeros still clears its T row
-        continue;
-      }
-      bucket[1] += (uint32_t)(len / L);
-      if (len % L) bucket[L - (uint32_t)(len % L) + 1]++;
-    }
-    for (uint32_t b = 1; b < L + 2; ++b) bucket[b] += bucket[b - 1];
-    const uint32_t tile_segs = bucket[L + 1];
-    for (uint32_t r = 0; r < R; ++r) {
-      if (skipped(r)) continue;
-      const uint64_t b0 = pt[r], len = pt[r + 1] - pt[r];
-      if (len == 0) {
-        if (t == 0 && segcnt[r] == 0) {
-          const uint32_t pos = base + bucket[L]++;
-          w.seg[pos] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, 0u);
-          w.seg_out[pos] = r;
-        }
-        continue;
-      }
-      const uint32_t cnt = (uint32_t)((len + L - 1) / L);
-      for (uint32_t q = 0; q < cnt; ++q) {
-        const uint64_t sb = b0 + (uint64_t)q * L;
-        const uint32_t sl = (uint32_t)std::min<uint64_t>(L, len - (uint64_t)q * L);
-        const uint32_t pos = base + bucket[L - sl]++;
-        w.seg[pos] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
-        w.seg_out[pos] = segcnt[r] == 1 ? r : R + first[r] + next[r]++;
-      }
-    }
-    base += tile_segs;
-  }
-  w.nsegs = nsegs; w.nslots = nslots; w.nmulti = nmulti;
-  *out = w;
-  return 0;
+  const uint64_t b = worklist_seg_bound(nnz, R, ntiles, L);
+  return 6 * pad256((size_t)R * 4) + pad256(b * 16) + 5 * pad256(b * 4) + 2 * pad256(cub_bytes) + pad256(4 * (6 + 2 * kMaxChunks)) + 8192;
 }
 
-// pinned host work list -> the side's device work list (async on the ctx stream)
-int upload_worklist(hpf_ctx *c, Side &s, const HostWorkList &h, const uint32_t *d_idx, const uint8_t *d_y)
+int build_worklist_device(hpf_ctx *c, Arena &dev, Arena &pin, Side &s, const uint64_t *d_run, uint32_t ntiles, uint64_t nnz,
+                          const uint32_t *d_skip_slot, uint32_t nchunks, const uint32_t *d_idx, const uint8_t *d_y,
+                          size_t cub_bytes, WlPending *pend)
 {
+  const uint32_t R = s.R, L = c->seg_len;
   WorkList &w = s.wl;
   w.idx = d_idx; w.y = d_y;
-  TRY(ensure(c, &w.seg, &w.seg_cap, h.nsegs));
-  TRY(ensure(c, &w.seg_out, &w.seg_out_cap, h.nsegs));
-  TRY(ensure(c, &w.multi_row, &w.multi_cap[0], h.nmulti));
-  TRY(ensure(c, &w.multi_first, &w.multi_cap[1], h.nmulti));
-  TRY(ensure(c, &w.multi_cnt, &w.multi_cap[2], h.nmulti));
-  w.nsegs = h.nsegs; w.npartial = h.nslots; w.nmulti = h.nmulti;
-  CU(cudaMemcpyAsync(w.seg, h.seg, sizeof(uint4) * h.nsegs, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(w.seg_out, h.seg_out, 4 * (size_t)h.nsegs, cudaMemcpyHostToDevice, c->stream));
-  if (h.nmulti) {
-    CU(cudaMemcpyAsync(w.multi_row, h.multi_row, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(w.multi_first, h.multi_first, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(w.multi_cnt, h.multi_cnt, 4 * (size_t)h.nmulti, cudaMemcpyHostToDevice, c->stream));
-  }
-  TRY(ensure(c, &s.Tpart, &s.tpart_cap, (size_t)h.nslots * c->ld));
-  if (c->bias) TRY(ensure(c, &s.Tbpart, &s.tbpart_cap, h.nslots));
+  nchunks = std::max(1u, std::min(std::min(nchunks, kMaxChunks), R));
+  const uint32_t chunk_rows = (R + nchunks - 1) / nchunks;
+  nchunks = (R + chunk_rows - 1) / chunk_rows;
+  if ((uint64_t)nchunks * ntiles * (L + 1) >= 0xffffffffull) return fail(c, HPF_EINVAL, "work-list keys do not fit 32 bits (%u chunks x %u tiles)", nchunks, ntiles);
+  const uint64_t bound64 = worklist_seg_bound(nnz, R, ntiles, L);
+  if (bound64 >= 0xfffffff0ull) return fail(c, HPF_EINVAL, "too many work segments (%llu)", (unsigned long long)bound64);
+  const uint32_t bound = (uint32_t)bound64;
+  TRY(ensure(c, &w.seg, &w.seg_cap, bound));
+  TRY(ensure(c, &w.seg_out, &w.seg_out_cap, bound));
+  const size_t multi_bound = std::min<size_t>(R, bound / 2 + 1);
+  TRY(ensure(c, &w.multi_row, &w.multi_cap[0], multi_bound));
+  TRY(ensure(c, &w.multi_first, &w.multi_cap[1], multi_bound));
+  TRY(ensure(c, &w.multi_cnt, &w.multi_cap[2], multi_bound));
+  WlArgs a;
+  a.run_ptr = d_run; a.R = R; a.ntiles = ntiles; a.L = L; a.chunk_rows = chunk_rows; a.skip_slot = d_skip_slot;
+  a.segcnt = dev.get<uint32_t>(R); a.multicnt = dev.get<uint32_t>(R); a.ismulti = dev.get<uint32_t>(R);
+  a.seg_off = dev.get<uint32_t>(R); a.first_off = dev.get<uint32_t>(R); a.multi_off = dev.get<uint32_t>(R);
+  a.seg_u = dev.get<uint4>(bound); a.out_u = dev.get<uint32_t>(bound); a.key_u = dev.get<uint32_t>(bound);
+  a.multi_row = w.multi_row; a.multi_first = w.multi_first; a.multi_cnt = w.multi_cnt;
+  uint32_t *key_s = dev.get<uint32_t>(bound), *perm_in = dev.get<uint32_t>(bound), *perm_out = dev.get<uint32_t>(bound);
+  void *d_tmp = dev.get<char>(cub_bytes);
+  const uint32_t ninfo = 4 + 2 * (nchunks + 1);
+  uint32_t *d_info = dev.get<uint32_t>(ninfo);
+  pend->h_info = pin.get<uint32_t>(ninfo);
+  pend->nchunks = nchunks; pend->chunk_rows = chunk_rows;
+  if (!a.segcnt || !a.multicnt || !a.ismulti || !a.seg_off || !a.first_off || !a.multi_off || !a.seg_u || !a.out_u || !a.key_u ||
+      !key_s || !perm_in || !perm_out || !d_tmp || !d_info || !pend->h_info)
+    return fail(c, HPF_ENOMEM, "set-up arena too small (work list)");
+  const unsigned rb = (R + 255) / 256, sb = (bound + 255) / 256;
+  CU(cudaMemsetAsync(a.key_u, 0xff, (size_t)bound * 4, c->stream)); // unused slots sort behind every segment
+  wl_count_kernel<<<rb, 256, 0, c->stream>>>(a);
+  size_t tb = cub_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, (const uint32_t *)a.segcnt, a.seg_off, (int64_t)R, c->stream));
+  tb = cub_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, (const uint32_t *)a.multicnt, a.first_off, (int64_t)R, c->stream));
+  tb = cub_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(d_tmp, tb, (const uint32_t *)a.ismulti, a.multi_off, (int64_t)R, c->stream));
+  wl_emit_kernel<<<rb, 256, 0, c->stream>>>(a);
+  iota_kernel<<<sb, 256, 0, c->stream>>>(perm_in, bound);
+  tb = cub_bytes;
+  CU(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const uint32_t *)a.key_u, key_s, (const uint32_t *)perm_in, perm_out, (int64_t)bound, 0, 32, c->stream));
+  wl_info_kernel<<<1, 32, 0, c->stream>>>(a, key_s, nchunks, d_info);
+  wl_gather_kernel<<<sb, 256, 0, c->stream>>>(perm_out, a.seg_u, a.out_u, d_info, w.seg, w.seg_out);
+  c->launches += 5;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pend->h_info, d_info, (size_t)ninfo * 4, cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
 
-// Device half of one orientation: order the nonzeros by (tile of col, row) -- the
-// gathered-side index and the rating permuted accordingly -- and leave the run
-// pointers in pinned host memory (async).  d_row / d_col / d_y are per nonzero in
-// the caller's CSR order.  presorted: the input is already ordered by row.
+// after the stream has been synchronised: counts into the side's work list, partial-sum slots sized
+int finish_worklist(hpf_ctx *c, Side &s, const WlPending &p)
+{
+  WorkList &w = s.wl;
+  w.nsegs = p.h_info[0]; w.npartial = p.h_info[1]; w.nmulti = p.h_info[2];
+  w.nchunks = p.nchunks; w.chunk_rows = p.chunk_rows;
+  for (uint32_t q = 0; q <= p.nchunks; ++q) {
+    w.chunk_seg[q] = p.h_info[4 + q];
+    w.chunk_multi[q] = p.h_info[4 + p.nchunks + 1 + q];
+  }
+  TRY(ensure(c, &s.Tpart, &s.tpart_cap, (size_t)w.npartial * c->ld));
+  if (c->bias) TRY(ensure(c, &s.Tbpart, &s.tbpart_cap, w.npartial));
+  return 0;
+}
+
+// One orientation of the ratings on the device: the nonzeros ordered by (tile of col, row), the
+// gathered-side index and the rating permuted accordingly, and the run pointers (run (t, r) at
+// d_run[t * R + r]).  d_row / d_col / d_y are per nonzero in the caller's order.  presorted: the input is
+// already ordered by row and d_rowptr is its row pointer -- with one tile that IS the orientation.
 struct Orientation {
   uint32_t ntiles = 1, tile_cols = 0;
-  bool from_host_rowptr = false; // presorted and one tile: the CSR itself, nothing to do on the device
-  uint64_t *h_run = nullptr;     // pinned, ntiles * R + 1 (when asked for)
-  uint64_t *d_run = nullptr;     // the same on the device (set-up arena)
+  const uint64_t *d_run = nullptr; // device, ntiles * R + 1
   const uint32_t *d_idx = nullptr;
   const uint8_t *d_y = nullptr;
 };
 
 size_t orientation_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, size_t cub_bytes)
 {
-  return 4 * pad256(nnz * 4) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
+  return 2 * pad256(nnz * 4) + 2 * pad256(nnz * 8) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
 }
 
-int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, uint64_t nnz, const uint32_t *d_row, const uint32_t *d_col,
-                  const uint8_t *d_y, bool presorted, uint32_t R, uint32_t C, uint32_t force_tile_cols, bool want_host_run,
-                  uint32_t **own_idx, size_t *own_idx_cap, uint8_t **own_y, size_t *own_y_cap, size_t cub_bytes, Orientation *o)
+int orient_device(hpf_ctx *c, Arena &dev, uint64_t nnz, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y,
+                  bool presorted, const uint64_t *d_rowptr, uint32_t R, uint32_t C, uint32_t **own_idx, size_t *own_idx_cap,
+                  uint8_t **own_y, size_t *own_y_cap, size_t cub_bytes, Orientation *o)
 {
-  if (force_tile_cols) {
-    o->tile_cols = force_tile_cols;
-    o->ntiles = (uint32_t)(((uint64_t)C + force_tile_cols - 1) / force_tile_cols);
-  } else {
-    o->ntiles = tiles_for(c, C, R, nnz);
-    o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
-  }
+  o->ntiles = tiles_for(c, C, R, nnz);
+  o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
   if (presorted && o->ntiles == 1) {
-    o->from_host_rowptr = true;
-    o->d_idx = d_col; o->d_y = d_y;
+    o->d_run = d_rowptr; o->d_idx = d_col; o->d_y = d_y;
     return 0;
   }
   const size_t nruns = (size_t)o->ntiles * R;
-  if (want_host_run) {
-    o->h_run = pin.get<uint64_t>(nruns + 1);
-    if (!o->h_run) return fail(c, HPF_ENOMEM, "pinned run-pointer arena too small");
-  }
   TRY(ensure(c, own_idx, own_idx_cap, nnz));
   if (d_y) TRY(ensure(c, own_y, own_y_cap, nnz));
   o->d_idx = *own_idx; o->d_y = d_y ? *own_y : nullptr;
@@ -750,85 +719,21 @@ int orient_device(hpf_ctx *c, Arena &dev, Arena &pin, uint64_t nnz, const uint32
   o->d_run = d_run;
   if (nnz == 0) {
     CU(cudaMemsetAsync(d_run, 0, (nruns + 1) * 8, c->stream));
-    if (want_host_run) memset(o->h_run, 0, (nruns + 1) * 8);
     return 0;
   }
-  uint32_t *perm = dev.get<uint32_t>(nnz), *perm2 = dev.get<uint32_t>(nnz), *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz);
+  uint32_t *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz);
+  uint64_t *val = dev.get<uint64_t>(nnz), *val2 = dev.get<uint64_t>(nnz);
   void *d_tmp = dev.get<char>(cub_bytes);
-  if (!perm || !perm2 || !key || !key2 || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  if (!key || !key2 || !val || !val2 || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
   size_t tmp_bytes = cub_bytes;
   const unsigned nb = (unsigned)((nnz + 255) / 256);
-  iota_kernel<<<nb, 256, 0, c->stream>>>(perm, nnz);
-  c->launches++;
-  if (!presorted) { // stable sort by row
-    CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_row, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0, bits_for(R), c->stream));
-    std::swap(perm, perm2);
-  }
-  if (o->ntiles > 1) { // then stable sort by the tile of the gathered-side index
-    gather_key_kernel<<<nb, 256, 0, c->stream>>>(perm, d_col, o->tile_cols, nnz, key);
-    c->launches++;
-    CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint32_t *)perm, perm2, (int64_t)nnz, 0,
-                                       bits_for(o->ntiles), c->stream));
-    std::swap(perm, perm2);
-  }
-  apply_perm_kernel<<<nb, 256, 0, c->stream>>>(perm, d_row, d_col, d_y, o->tile_cols, R, nnz, *own_idx, d_y ? *own_y : nullptr, key);
-  run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key, nnz, (uint32_t)nruns, d_run);
-  c->launches += 2;
-  CU(cudaGetLastError());
-  if (want_host_run) CU(cudaMemcpyAsync(o->h_run, d_run, (nruns + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-  return 0;
-}
-
-// ---- tile-sweep work list, built on the device ------------------------------------
-// phase 1: segments per run and their prefix sum; the total lands in pinned memory
-struct TileCount {
-  uint32_t *cnt = nullptr, *off = nullptr;
-  uint32_t *h_last = nullptr; // pinned {off[nruns-1], cnt[nruns-1]}
-  uint64_t nruns = 0;
-};
-int tile_count(hpf_ctx *c, Arena &dev, Arena &pin, const uint64_t *d_run, uint64_t nruns, TileCount *tc)
-{
-  tc->nruns = nruns;
-  tc->cnt = dev.get<uint32_t>(nruns);
-  tc->off = dev.get<uint32_t>(nruns);
-  tc->h_last = pin.get<uint32_t>(2);
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)nruns, c->stream);
-  void *d_tmp = dev.get<char>(scan_bytes);
-  if (!tc->cnt || !tc->off || !tc->h_last || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (tile count)");
-  tc->h_last[0] = tc->h_last[1] = 0;
-  if (nruns == 0) return 0;
-  seg_count_kernel<<<(unsigned)((nruns + 255) / 256), 256, 0, c->stream>>>(d_run, nruns, c->seg_len, tc->cnt);
-  CU(cub::DeviceScan::ExclusiveSum(d_tmp, scan_bytes, (const uint32_t *)tc->cnt, tc->off, (int64_t)nruns, c->stream));
-  c->launches += 1;
-  CU(cudaMemcpyAsync(&tc->h_last[0], tc->off + nruns - 1, 4, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(&tc->h_last[1], tc->cnt + nruns - 1, 4, cudaMemcpyDeviceToHost, c->stream));
-  return 0;
-}
-// phase 2 (after the total is known): emit, sort by (tile, descending length), tile pointers
-int tile_emit(hpf_ctx *c, Arena &scratch, const uint64_t *d_run, const TileCount &tc, uint32_t R, uint32_t ntiles, uint32_t nsegs, TilePlan *tp)
-{
-  tp->nsegs = nsegs; tp->ntiles = ntiles;
-  TRY(ensure(c, &tp->seg, &tp->seg_cap, nsegs));
-  TRY(ensure(c, &tp->tile_ptr, &tp->tile_ptr_cap, (size_t)ntiles + 1));
-  if (nsegs == 0) {
-    CU(cudaMemsetAsync(tp->tile_ptr, 0, ((size_t)ntiles + 1) * 4, c->stream));
-    return 0;
-  }
-  const uint32_t L = c->seg_len;
-  size_t sort_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint4 *)nullptr, (uint4 *)nullptr,
-                                  (int64_t)nsegs, 0, 32, c->stream);
-  TRY(arena_reserve(c, scratch, pad256((size_t)nsegs * 16) + 2 * pad256((size_t)nsegs * 4) + pad256(sort_bytes) + 4096));
-  uint4 *seg_u = scratch.get<uint4>(nsegs);
-  uint32_t *key_u = scratch.get<uint32_t>(nsegs), *key_s = scratch.get<uint32_t>(nsegs);
-  void *d_tmp = scratch.get<char>(sort_bytes);
-  if (!seg_u || !key_u || !key_s || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (tile emit)");
-  seg_emit_kernel<<<(unsigned)((tc.nruns + 255) / 256), 256, 0, c->stream>>>(d_run, tc.off, tc.nruns, R, L, seg_u, key_u);
-  CU(cub::DeviceRadixSort::SortPairs(d_tmp, sort_bytes, (const uint32_t *)key_u, key_s, (const uint4 *)seg_u, tp->seg, (int64_t)nsegs, 0,
-                                     bits_for((uint64_t)ntiles * (L + 1)), c->stream));
-  tile_ptr_kernel<<<(nsegs + 256) / 256, 256, 0, c->stream>>>(key_s, nsegs, L + 1, ntiles, tp->tile_ptr);
-  c->launches += 2;
+  // one stable sort by (tile of the gathered-side index, row); the payload carries that index and the rating
+  orient_key_kernel<<<nb, 256, 0, c->stream>>>(d_row, d_col, d_y, o->tile_cols, R, nnz, key, val);
+  CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint64_t *)val, val2, (int64_t)nnz, 0,
+                                     bits_for((uint64_t)nruns), c->stream));
+  orient_unpack_kernel<<<nb, 256, 0, c->stream>>>(val2, nnz, *own_idx, d_y ? *own_y : nullptr);
+  run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key2, nnz, (uint32_t)nruns, d_run);
+  c->launches += 3;
   CU(cudaGetLastError());
   return 0;
 }
@@ -915,12 +820,66 @@ int ensure_aux(hpf_ctx *c)
   return 0;
 }
 
-// one CAVI iteration; order of hgaprec.cc:1340-1414 (hier), 928-956 (vb),
-// 1227-1297 (vb_bias, both orderings)
-#define MARK(i) do { if (c->profiling) CU(cudaEventRecord(c->pev[i], c->stream)); } while (0)
+// ---- collectives: all on comm_stream, ordered against the compute stream through events ---------------------
+int nccl_fail(hpf_ctx *c, int rc, const char *what)
+{
+  return fail(c, HPF_ENCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+}
+
+// in-place sum over the ranks of `count` floats at p, enqueued on comm_stream (the caller has made comm_stream
+// wait for the producer)
+int comm_allreduce(hpf_ctx *c, float *p, size_t count)
+{
+  if (count == 0) return 0;
+  const int rc = g_nccl.AllReduce(p, p, count, ncclFloat32, ncclSum, c->comm, c->comm_stream);
+  return rc == ncclSuccess ? 0 : nccl_fail(c, rc, "ncclAllReduce");
+}
+
+// one CAVI iteration; order of hgaprec.cc:1340-1414 (hier), 928-956 (vb), 1227-1297 (vb_bias, both orderings).
+// The two sweeps are independent of each other (both read the previous expectations), so their order is free:
+//   no dense head:  item pass (chunk by chunk) -> user pass -> theta update -> beta update
+//   dense head:     user pass -> head (adds to T_theta, writes the head items' T_beta rows) -> item pass -> ...
+// Multi-GPU: the all-reduce of a chunk's T_beta rows starts on comm_stream as soon as the chunk's sweep and combine
+// are done and runs under everything that follows on the compute stream; the tail [Tb_beta | sum_u E[theta] | flag]
+// follows the theta update; the beta update waits for comm_stream.
+// Profiling events come in pairs (begin, end) per stage: 0 user pass, 1 item pass, 2 combine (theta), 3 dense head,
+// 4 theta update, 5 exposed wait for the collectives, 6 beta update, 7 whole iteration.
+#define STAGE_BEGIN(i) do { if (c->profiling) CU(cudaEventRecord(c->pev[2 * (i)], c->stream)); } while (0)
+#define STAGE_END(i) do { if (c->profiling) CU(cudaEventRecord(c->pev[2 * (i) + 1], c->stream)); } while (0)
+
+int user_pass(hpf_ctx *c)
+{
+  STAGE_BEGIN(0);
+  TRY(launch_sweep(c, c->th, c->be)); // CSR rows = users (the tail items when the head runs dense): T_theta
+  STAGE_END(0);
+  STAGE_BEGIN(2);
+  TRY(launch_combine(c, c->th));
+  STAGE_END(2);
+  return 0;
+}
+
+int item_pass(hpf_ctx *c)
+{
+  const bool mg = c->nranks > 1;
+  const WorkList &w = c->be.wl;
+  STAGE_BEGIN(1);
+  for (uint32_t q = 0; q < w.nchunks; ++q) {
+    TRY(launch_sweep(c, c->be, c->th, (int)q)); // CSC rows = items of chunk q: T_beta (local users only)
+    TRY(launch_combine(c, c->be, (int)q));
+    if (mg) { // rows [r0, r1) of T_beta are final on this rank: sum them over the ranks under what follows
+      const size_t r0 = (size_t)q * w.chunk_rows, r1 = std::min<size_t>((size_t)(q + 1) * w.chunk_rows, c->be.R);
+      CU(cudaEventRecord(c->ev_chunk[q], c->stream));
+      CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[q], 0));
+      TRY(comm_allreduce(c, c->be.T + r0 * c->ld, (r1 - r0) * c->ld));
+    }
+  }
+  STAGE_END(1);
+  return 0;
+}
 
 int one_iteration(hpf_ctx *c)
 {
+  const bool mg = c->nranks > 1;
   if (c->logl && c->hier) { // logl() sees the rate priors of THIS iteration's set_prior_rate (gpbase.hh:163-173)
     CU(cudaMemcpyAsync(c->th.pr_shape_prev, c->th.pr_shape, sizeof(float) * c->th.R, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->th.pr_rate_prev, c->th.pr_rate, sizeof(float) * c->th.R, cudaMemcpyDeviceToDevice, c->stream));
@@ -928,64 +887,50 @@ int one_iteration(hpf_ctx *c)
     CU(cudaMemcpyAsync(c->be.pr_rate_prev, c->be.pr_rate, sizeof(float) * c->be.R, cudaMemcpyDeviceToDevice, c->stream));
     c->pr_prev_valid = true;
   }
-  MARK(0);
-  TRY(launch_sweep(c, c->th, c->be)); // user pass (CSR; the tail items when the head runs as a tile sweep): T_theta
-  MARK(1);
-  if (c->item_tile.on) { // item pass as a tile sweep over user blocks: T_beta accumulated with reductions
-    const size_t mk = (size_t)c->be.R * c->ld, mpad = c->bias ? (((size_t)c->be.R + 3) & ~(size_t)3) : 0;
-    CU(cudaMemsetAsync(c->redblock, 0, (mk + mpad) * sizeof(float), c->stream));
-    TRY(launch_tile_sweep(c, c->item_tile, c->be, c->th));
+  STAGE_BEGIN(7);
+  if (c->dense.on) {
+    TRY(user_pass(c));
+    STAGE_BEGIN(3);
+    TRY(launch_dense_head(c)); // the dense head block on tcgen05: T_theta +=, T_beta[head items] =
+    STAGE_END(3);
+    TRY(item_pass(c));
   } else {
-    TRY(launch_sweep(c, c->be, c->th)); // item pass (CSC): T_beta (local users only)
+    TRY(item_pass(c));
+    TRY(user_pass(c));
   }
-  MARK(2);
-  TRY(launch_combine(c, c->th));
-  TRY(launch_combine(c, c->be));
-  MARK(3);
-  TRY(launch_tile_sweep(c, c->head_tile, c->th, c->be)); // user pass, head items from shared memory: T_theta +=
-  TRY(launch_dense_head(c)); // or the dense head block on tcgen05: T_theta +=, T_beta[head items] +=
-  MARK(7);
   const double n_glob = c->cfg.n_users_global ? (double)c->cfg.n_users_global : (double)c->cfg.n_users;
   if (c->jacobi) { // -novb: beta's rate uses the OLD (global) sum_u E[theta], hgaprec.cc:1278-1283
-    if (c->nranks > 1 && !c->th_colsum_global) {
-      int rc = g_nccl.AllReduce(c->th.colsum, c->th.colsum, c->Kp, ncclFloat32, ncclSum, c->comm, c->stream);
-      if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclAllReduce(colsum): %d", rc);
+    if (mg && !c->th_colsum_global) { // first iteration after hpf_set_state: the local sums have not been reduced yet
+      CU(cudaEventRecord(c->ev_theta, c->stream));
+      CU(cudaStreamWaitEvent(c->comm_stream, c->ev_theta, 0));
+      TRY(comm_allreduce(c, c->th.colsum, c->Kp));
+      CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+      CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     }
     CU(cudaMemcpyAsync(c->colsum_theta_old, c->th.colsum, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
   }
-  // HPF_AR_OVERLAP: T_beta and Tb_beta are final here, sum_u E[theta] is not.  Their all-reduce starts now on the
-  // second stream and runs under the theta update (which touches neither; its column sums land in the last Kp
-  // floats of the block, outside this reduction); the Kp column sums follow on the main stream.  The two
-  // reductions never overlap each other: each waits for the other's stream through an event.
-  const bool overlap = c->ar_overlap && c->nranks > 1 && !c->jacobi && !c->profiling;
-  if (overlap) {
-    CU(cudaEventRecord(c->ev_tbeta, c->stream));
-    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_tbeta, 0));
-    int rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count - c->Kp, ncclFloat32, ncclSum, c->comm, c->comm_stream);
-    if (rc != ncclSuccess)
-      return fail(c, HPF_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
-    CU(cudaEventRecord(c->ev_ar, c->comm_stream));
-  }
   // theta: rate from the old beta column sums (Gauss-Seidel and Jacobi alike)
+  STAGE_BEGIN(4);
   TRY(launch_update(c, c->th, c->be.colsum, (double)c->cfg.n_items));
-  MARK(4);
-  if (c->nranks > 1) {
-    int rc;
-    if (overlap) {
-      CU(cudaStreamWaitEvent(c->stream, c->ev_ar, 0));
-      rc = g_nccl.AllReduce(c->th.colsum, c->th.colsum, c->Kp, ncclFloat32, ncclSum, c->comm, c->stream);
-    } else {
-      // [T_beta | Tb_beta | colsum_theta] summed over the user shards, in place
-      rc = g_nccl.AllReduce(c->redblock, c->redblock, c->red_count, ncclFloat32, ncclSum, c->comm, c->stream);
-    }
-    if (rc != ncclSuccess)
-      return fail(c, HPF_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  STAGE_END(4);
+  STAGE_BEGIN(5);
+  if (mg) {
+    // [Tb_beta | sum_u E[theta] | fallback flag] summed over the user shards; with mg_exact also the item side's
+    // fallback buffers [Tdirect_beta | Tbdirect_beta]
+    CU(cudaEventRecord(c->ev_theta, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_theta, 0));
+    TRY(comm_allreduce(c, c->red_tail, c->red_tail_count));
+    if (c->mg_exact) TRY(comm_allreduce(c, c->redblock2, c->red2_count));
+    CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     c->th_colsum_global = true;
   }
+  STAGE_END(5);
   // beta: Gauss-Seidel uses the NEW sum_u E[theta] (hgaprec.cc:1380-1384), -novb the old one
-  MARK(5);
+  STAGE_BEGIN(6);
   TRY(launch_update(c, c->be, c->jacobi ? c->colsum_theta_old : c->th.colsum, n_glob));
-  MARK(6);
+  STAGE_END(6);
+  STAGE_END(7);
   c->iterations++;
   return 0;
 }
@@ -1038,6 +983,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (cfg->abi_version != HPF_ABI_VERSION) return fail(c, HPF_EINVAL, "abi_version %u != %u", cfg->abi_version, HPF_ABI_VERSION);
   if (cfg->k == 0 || cfg->k > 1024) return fail(c, HPF_EINVAL, "k=%u out of range [1,1024]", cfg->k);
   if (cfg->n_items == 0) return fail(c, HPF_EINVAL, "n_items must be > 0");
+  if (cfg->n_users == 0) return fail(c, HPF_EINVAL, "n_users must be > 0 (an empty user shard: use fewer ranks)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(c, HPF_ENODEVICE, "no CUDA device available (libhpf_b200 has no CPU path)");
@@ -1056,26 +1002,11 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (const char *e = getenv("HPF_L2_TILE_MB")) { int v = atoi(e); if (v >= 0 && v <= 4096) n->l2_tile_bytes = (uint64_t)v << 20; }
   if (const char *e = getenv("HPF_L2_TILE_KB")) { int v = atoi(e); if (v >= 0) { n->l2_tile_bytes = (uint64_t)v << 10; n->l2_tile_forced = true; } } // tests
   pick_sweep_shape(n);
-  {
-    // rows per shared-memory tile of the tile sweeps (packed K4 float4 per row, + bias terms)
-    int smem_optin = 0;
-    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    const size_t budget = smem_optin > 16384 ? (size_t)smem_optin - 2048 : 0;
-    const size_t per_row = (size_t)n->K4 * 16 + (n->bias ? 8 : 0);
-    uint32_t tr = (uint32_t)std::min<size_t>(budget / per_row, 4096);
-    tr &= ~31u;
-    n->tile_rows = tr >= 64 ? tr : 0; // too few rows per tile: tile sweeps off
-    n->tile_smem = (size_t)n->tile_rows * per_row;
-    if (const char *e = getenv("HPF_ITEM_TILE")) n->item_tile_mode = atoi(e);
-    if (const char *e = getenv("HPF_HEAD_TILE")) n->head_tile_mode = atoi(e);
-    if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
-    if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
-    if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 7;
-    if (const char *e = getenv("HPF_TILE_ROWS")) { // tests: force small tiles
-      const uint32_t v = (uint32_t)atoi(e);
-      if (v >= 1 && v <= n->tile_rows) { n->tile_rows = v; n->tile_smem = (size_t)v * per_row; }
-    }
-  }
+  if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
+  if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
+  if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 7;
+  if (const char *e = getenv("HPF_AR_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= (int)kMaxChunks) n->ar_chunks = v; }
+  if (const char *e = getenv("HPF_MG_EXACT")) n->mg_exact = atoi(e) != 0; // tests: fallback buffers inside the all-reduce from the start
   c = n;
   int rc = 0;
   do {
@@ -1088,15 +1019,23 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     c->be.prior_shape = cfg->beta_shape; c->be.prior_rate = cfg->beta_rate;
     c->be.pr_prior_shape = cfg->betarate_shape; c->be.pr_prior_rate = cfg->betarate_rate;
     c->be.bias_prior_shape = cfg->betabias_shape; c->be.bias_prior_rate = cfg->betabias_rate;
-    if ((rc = alloc_side(c, c->th, cfg->n_users))) break;
-    if ((rc = alloc_side(c, c->be, cfg->n_items))) break;
-    // item-side reduce block: [T_beta (m x ld) | Tb_beta (m, padded to 4) | colsum_theta (Kp)]
+    if ((rc = alloc_side(c, c->th, cfg->n_users, true))) break;
+    if ((rc = alloc_side(c, c->be, cfg->n_items, false))) break;
+    // item-side reduce blocks: [T_beta (m x ld) | Tb_beta (m, padded to 4) | colsum_theta (Kp) | flag (4)] and
+    // [Tdirect_beta (m x ld) | Tbdirect_beta (m, padded to 4)]
     const size_t mk = (size_t)cfg->n_items * c->ld, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
-    c->red_count = mk + mpad + c->Kp;
+    c->red_count = mk + mpad + c->Kp + 4;
     if ((rc = dalloc(c, &c->redblock, c->red_count))) break;
     c->be.T = c->redblock;
     c->be.Tb = c->bias ? c->redblock + mk : nullptr;
     c->th.colsum = c->redblock + mk + mpad;
+    c->red_tail = c->redblock + mk; c->red_tail_count = mpad + c->Kp + 4;
+    c->red_flag = c->redblock + mk + mpad + c->Kp;
+    c->red2_count = mk + mpad;
+    if ((rc = dalloc(c, &c->redblock2, c->red2_count))) break;
+    c->be.Tdirect = c->redblock2;
+    c->be.Tbdirect = c->bias ? c->redblock2 + mk : nullptr;
+    if ((rc = dalloc(c, &c->mg_fired, 4))) break;
     if ((rc = dalloc(c, &c->be.colsum, c->Kp))) break;
     if ((rc = dalloc(c, &c->th.T, (size_t)cfg->n_users * c->ld))) break;
     if (c->bias && (rc = dalloc(c, &c->th.Tb, cfg->n_users))) break;
@@ -1129,12 +1068,12 @@ void hpf_destroy(hpf_ctx *c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  if (c->ev_tbeta) cudaEventDestroy(c->ev_tbeta);
-  if (c->ev_ar) cudaEventDestroy(c->ev_ar);
+  for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
+  if (c->ev_theta) cudaEventDestroy(c->ev_theta);
+  if (c->ev_comm) cudaEventDestroy(c->ev_comm);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (auto &p : c->allocs) cudaFree(p.first);
   if (c->dev_arena.base) cudaFree(c->dev_arena.base);
-  if (c->dev_arena2.base) cudaFree(c->dev_arena2.base);
   if (c->pin_arena.base) cudaFreeHost(c->pin_arena.base);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1157,30 +1096,30 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   Trace tr(c->stream);
   c->ratings_set = false;
   c->nnz = nnz;
-  c->item_tile.on = c->head_tile.on = false;
   c->pin_arena.pinned_host = true;
-  const uint32_t L = c->seg_len, TR = c->tile_rows;
+  const uint32_t L = c->seg_len;
   const uint32_t th_t = tiles_for(c, m, n, nnz), be_t = tiles_for(c, n, m, nnz);
-  // the item pass can run as a tile sweep over blocks of TR users when the run keys fit 32 bits
-  const uint64_t it_tiles = TR ? ((uint64_t)n + TR - 1) / TR : 0;
-  const bool try_item_tile = c->item_tile_mode != 0 && TR > 0 && nnz > 0 && it_tiles * m < 0xfffffff0ull;
-  const bool try_head_tile = c->head_tile_mode != 0 && TR > 0 && nnz > 0;
-  const bool try_dense = c->dense_head_mode != 0 && c->Kp + (c->bias ? 2u : 0u) <= (uint32_t)head::kFact && nnz > 0 && !try_item_tile;
-  const bool want_deg = try_head_tile || try_dense;
+  const bool try_dense = c->dense_head_mode != 0 && c->Kp + (c->bias ? 2u : 0u) <= (uint32_t)head::kFact && nnz > 0;
   c->dense.on = false;
+  // chunks of the item pass (multi-GPU: one all-reduce per chunk, overlapped with the following sweeps).  A chunk
+  // should carry tens of MB so that the collective runs at bandwidth, and a launch per chunk must stay cheap.
+  uint32_t item_chunks = 1;
+  if (c->nranks > 1) {
+    const uint64_t payload = (uint64_t)m * c->ld * sizeof(float);
+    item_chunks = c->ar_chunks > 0 ? (uint32_t)c->ar_chunks : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, payload / (48ull << 20)));
+  }
   size_t cub_bytes = 0, scan_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int64_t)std::max<uint64_t>(nnz, 1), 0, 32, c->stream);
+  const uint64_t seg_bound = std::max(worklist_seg_bound(nnz, n, th_t, L), worklist_seg_bound(nnz, m, be_t, L));
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint64_t *)nullptr,
+                                  (uint64_t *)nullptr, (int64_t)std::max<uint64_t>(std::max<uint64_t>(nnz, 1), seg_bound), 0, 32, c->stream);
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                (int64_t)std::max<uint64_t>(std::max<uint64_t>(nnz + 1, it_tiles * m), n), c->stream);
-  const size_t item_runs = try_item_tile ? (size_t)it_tiles * m : 0;
+                                (int64_t)std::max<uint64_t>(std::max<uint64_t>(nnz + 1, m), n), c->stream);
+  cub_bytes = std::max(cub_bytes, scan_bytes);
   const size_t dev_need = pad256(((size_t)n + 1) * 8) + pad256(nnz * 4) + 8 * pad256((size_t)m * 4) +
-                          orientation_dev_bytes(nnz, m, (uint32_t)std::max<uint64_t>(be_t, it_tiles ? it_tiles : 1), cub_bytes) +
                           orientation_dev_bytes(nnz, m, be_t, cub_bytes) + orientation_dev_bytes(nnz, n, th_t, cub_bytes) +
-                          2 * pad256(item_runs * 4) + 2 * pad256((size_t)n * 4 + 4) +
-                          2 * pad256((nnz + 1) * 4) + 2 * pad256(((size_t)n + 1) * 8) + 3 * pad256(scan_bytes) + (1u << 16);
-  const size_t pin_need = pad256(((size_t)th_t * n + 1) * 8) + pad256(((size_t)be_t * m + 1) * 8) + pad256(((size_t)n + 1) * 8) +
-                          pad256((size_t)m * 4) + worklist_host_bytes(nnz, n, th_t, L) + worklist_host_bytes(nnz, m, be_t, L) + (1u << 16);
+                          worklist_dev_bytes(nnz, n, th_t, L, cub_bytes) + worklist_dev_bytes(nnz, m, be_t, L, cub_bytes) +
+                          2 * pad256((nnz + 1) * 4) + pad256(nnz * 4) + 2 * pad256(((size_t)n + 1) * 8) + 2 * pad256(cub_bytes) + (1u << 16);
+  const size_t pin_need = 2 * pad256((size_t)m * 4) + (1u << 16);
   TRY(arena_reserve(c, c->dev_arena, dev_need));
   TRY(arena_reserve(c, c->pin_arena, pin_need));
   TRY(ensure(c, &c->csr_idx, &c->csr_idx_cap, nnz));
@@ -1196,33 +1135,30 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   uint32_t *h_bad = pin.get<uint32_t>(1);
   if (!d_rowptr || !d_rowof || !h_bad) return fail(c, HPF_ENOMEM, "set-up arena too small");
   *h_bad = 0;
-  CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
+  CU(cudaMemsetAsync(c->scratch_u32, 0, 8, c->stream));
   const unsigned nb = (unsigned)((nnz + 255) / 256);
+  CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (nnz > 0) {
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
     if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    if (c->logl) { // hpf_elbo walks the ratings user by user
-      TRY(ensure(c, &c->csr_rowptr, &c->csr_rowptr_cap, (size_t)n + 1));
-      CU(cudaMemcpyAsync(c->csr_rowptr, d_rowptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
     check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32); // every item index must be < n_items
     expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
     c->launches += 2;
   }
+  if (c->logl) { // hpf_elbo walks the ratings user by user
+    TRY(ensure(c, &c->csr_rowptr, &c->csr_rowptr_cap, (size_t)n + 1));
+    CU(cudaMemcpyAsync(c->csr_rowptr, d_rowptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
   CU(cudaMemcpyAsync(h_bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
   // item pass ordering: rows = items, gathers user rows (users ascending inside a run)
   Orientation io, uo;
-  TileCount itc;
-  TRY(orient_device(c, dev, pin, nnz, c->csr_idx, d_rowof, d_y, false, m, n, try_item_tile ? TR : 0, !try_item_tile, &c->csc_idx,
-                    &c->csc_idx_cap, &c->csc_y, &c->csc_y_cap, cub_bytes, &io));
-  if (try_item_tile) TRY(tile_count(c, dev, pin, io.d_run, (uint64_t)io.ntiles * m, &itc));
-  // item degrees (from the item runs) and their descending order: the head items of the user pass
-  uint32_t *d_deg = nullptr, *d_degkey = nullptr, *d_degkey_s = nullptr, *d_id = nullptr, *d_id_s = nullptr, *h_degkey = nullptr;
-  uint32_t *h_headid = nullptr;
-  if (want_deg) {
-    d_deg = dev.get<uint32_t>(m); d_degkey = dev.get<uint32_t>(m); d_degkey_s = dev.get<uint32_t>(m);
-    d_id = dev.get<uint32_t>(m); d_id_s = dev.get<uint32_t>(m);
+  TRY(orient_device(c, dev, nnz, c->csr_idx, d_rowof, d_y, false, nullptr, m, n, &c->csc_idx, &c->csc_idx_cap, &c->csc_y,
+                    &c->csc_y_cap, cub_bytes, &io));
+  // item degrees (from the item runs) and their descending order: the candidates for the dense head
+  uint32_t *d_id_s = nullptr, *h_degkey = nullptr;
+  if (try_dense) {
+    uint32_t *d_deg = dev.get<uint32_t>(m), *d_degkey = dev.get<uint32_t>(m), *d_degkey_s = dev.get<uint32_t>(m), *d_id = dev.get<uint32_t>(m);
+    d_id_s = dev.get<uint32_t>(m);
     h_degkey = pin.get<uint32_t>(m);
     void *d_tmp = dev.get<char>(cub_bytes);
     if (!d_deg || !d_degkey || !d_degkey_s || !d_id || !d_id_s || !h_degkey || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (degrees)");
@@ -1231,39 +1167,21 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     size_t tb = cub_bytes;
     CU(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const uint32_t *)d_degkey, d_degkey_s, (const uint32_t *)d_id, d_id_s, (int64_t)m, 0, 32, c->stream));
     c->launches += 2;
-    CU(cudaMemcpyAsync(h_degkey, d_degkey_s, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
-    h_headid = pin.get<uint32_t>(kMaxHeadBlocks * head::kHead);
-    if (!h_headid) return fail(c, HPF_ENOMEM, "pinned arena too small");
-    CU(cudaMemcpyAsync(h_headid, d_id_s, (size_t)std::min<uint32_t>(m, kMaxHeadBlocks * head::kHead) * 4, cudaMemcpyDeviceToHost, c->stream));
+    const uint32_t ncand = std::min<uint32_t>(m, kMaxHeadBlocks * head::kHead);
+    CU(cudaMemcpyAsync(h_degkey, d_degkey_s, (size_t)ncand * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream)); // the head decision needs the degrees on the host
+    CU(cudaGetLastError());
+    tr.mark("stage 1: upload, item order");
+    if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
   }
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaGetLastError());
-  tr.mark("stage 1: upload, item order");
-  if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
 
-  // ================= decisions =================
-  uint32_t item_nsegs = 0;
-  bool item_tile = false;
-  if (try_item_tile) {
-    item_nsegs = itc.h_last[0] + itc.h_last[1];
-    // a segment costs one row-side load and one reduction; below ~3 nonzeros per segment the L2 gather is cheaper
-    item_tile = c->item_tile_mode == 1 || (item_nsegs > 0 && (double)nnz / item_nsegs >= 3.0);
-  }
-  uint32_t H = 0;
-  bool head_tile = false;
-  if (try_head_tile) {
-    H = std::min(TR, m);
-    uint64_t head_nnz = 0;
-    for (uint32_t r = 0; r < H; ++r) head_nnz += 0xffffffffu - h_degkey[r];
-    head_tile = c->head_tile_mode == 1 || (double)head_nnz >= 0.2 * (double)nnz;
-  }
-  // dense head on the tensor cores: the kHead most popular items, when they carry enough of the nonzeros
+  // ================= decision: dense head on the tensor cores =================
+  // blocks of 128 items by descending popularity: the first must carry >= 15 % of the nonzeros, every further
+  // one >= 6 % (a block costs one dense pass over all users whatever its density; measured break-even ~6 %)
   bool dense_head = false;
-  std::vector<uint8_t> skip_item;
-  if (try_dense && !head_tile) {
-    // blocks of 128 items by descending popularity: the first must carry >= 15 % of the nonzeros, every further
-    // one >= 6 % (a block costs one dense pass over all users whatever its density; measured break-even ~6 %)
-    uint64_t head_nnz = 0;
+  uint32_t H = 0;
+  uint64_t head_nnz = 0;
+  if (try_dense) {
     uint32_t nblk = 0;
     for (uint32_t b = 0; b < kMaxHeadBlocks && b * head::kHead < m; ++b) {
       uint64_t blk = 0;
@@ -1279,105 +1197,84 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
       H = std::min<uint32_t>(nblk * head::kHead, m);
       c->dense.head_nnz = head_nnz;
       c->dense.nblocks = nblk;
-      skip_item.assign(m, 0);
-      for (uint32_t r = 0; r < H; ++r) skip_item[h_headid[r]] = 1; // the item pass has no rows for head items
     }
   }
-  const bool split_head = head_tile || dense_head;
-  const std::vector<uint8_t> *skip_ptr = dense_head ? &skip_item : nullptr;
 
-  // ================= stage 2 (async): item work list; user-pass head / tail split =================
-  HostWorkList uw, iw;
-  if (item_tile) {
-    TRY(tile_emit(c, c->dev_arena2, io.d_run, itc, m, io.ntiles, item_nsegs, &c->item_tile));
-    to_slot_kernel<<<nb, 256, 0, c->stream>>>(c->csc_idx, nnz, TR);
-    c->launches++;
-    c->item_tile.on = true; c->item_tile.nnz = nnz; c->item_tile.tile0_count = 0;
-    c->item_tile.idx = c->csc_idx; c->item_tile.y = c->csc_y; c->item_tile.has_y = y != nullptr; // not owned: the item-ordered copy
-    c->item_tile.cpt = io.ntiles >= 4u * (uint32_t)c->sm_count ? 2u : std::max(2u, (8u * (uint32_t)c->sm_count + io.ntiles - 1) / io.ntiles);
-    // the gather kernel is not used for the item side: an empty work list
-    c->be.wl.nsegs = 0; c->be.wl.nmulti = 0; c->be.wl.npartial = 0;
-  } else if (try_item_tile) {
-    // fall back to the L2-tiled gather ordering (set-up cost only)
-    TRY(orient_device(c, dev, pin, nnz, c->csr_idx, d_rowof, d_y, false, m, n, 0, true, &c->csc_idx, &c->csc_idx_cap, &c->csc_y,
-                      &c->csc_y_cap, cub_bytes, &io));
-  }
-  uint64_t *h_tailptr = nullptr, *d_tailptr = nullptr, *d_headptr = nullptr;
-  TileCount htc;
-  uint64_t *h_counts = pin.get<uint64_t>(2); // {tail nnz, -}
-  uint32_t *h_yovf = nullptr;                // dense head: a cell of the byte matrix Y overflowed
-  if (!h_counts) return fail(c, HPF_ENOMEM, "pinned arena too small");
-  if (split_head) {
-    TilePlan &hp = c->head_tile;
-    if (head_tile) {
-      TRY(ensure(c, &hp.row_ids, &hp.row_ids_cap, H));
-      TRY(ensure(c, &hp.idx, &hp.idx_cap, nnz));
-      if (y) TRY(ensure(c, &hp.y, &hp.y_cap, nnz));
-    }
-    TRY(ensure(c, &c->tail_idx, &c->tail_idx_cap, nnz));
-    if (y) TRY(ensure(c, &c->tail_y, &c->tail_y_cap, nnz));
-    uint32_t *d_slot = dev.get<uint32_t>(m), *d_istail = dev.get<uint32_t>(nnz + 1), *d_tailpos = dev.get<uint32_t>(nnz + 1);
-    d_tailptr = dev.get<uint64_t>((size_t)n + 1); d_headptr = dev.get<uint64_t>((size_t)n + 1);
-    h_tailptr = pin.get<uint64_t>((size_t)n + 1);
-    void *d_tmp = dev.get<char>(scan_bytes);
-    if (!d_slot || !d_istail || !d_tailpos || !d_tailptr || !d_headptr || !h_tailptr || !d_tmp)
-      return fail(c, HPF_ENOMEM, "set-up arena too small (head split)");
-    if (head_tile) CU(cudaMemcpyAsync(hp.row_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+  // ================= stage 2 (async): work lists on the device; user-pass head / tail split =================
+  WlPending up, ip;
+  uint32_t *d_slot = nullptr; // slot_of[item] among the head items, 0xffffffff for the tail
+  uint32_t *h_yovf = nullptr; // dense head: a cell of the byte matrix Y overflowed
+  if (dense_head) {
+    d_slot = dev.get<uint32_t>(m);
+    if (!d_slot) return fail(c, HPF_ENOMEM, "set-up arena too small (head slots)");
     CU(cudaMemsetAsync(d_slot, 0xff, (size_t)m * 4, c->stream));
     head_slot_kernel<<<(H + 255) / 256, 256, 0, c->stream>>>(d_id_s, H, d_slot);
+    c->launches++;
+  }
+  // the item pass has no rows for head items: head_kernel produces their T_beta rows
+  TRY(build_worklist_device(c, dev, pin, c->be, io.d_run, io.ntiles, nnz, d_slot, item_chunks, io.d_idx, io.d_y, cub_bytes, &ip));
+  if (dense_head) {
+    const uint64_t ntail = nnz - head_nnz;
+    TRY(ensure(c, &c->tail_idx, &c->tail_idx_cap, nnz));
+    if (y) TRY(ensure(c, &c->tail_y, &c->tail_y_cap, nnz));
+    uint32_t *d_istail = dev.get<uint32_t>(nnz + 1), *d_tailpos = dev.get<uint32_t>(nnz + 1);
+    uint64_t *d_tailptr = dev.get<uint64_t>((size_t)n + 1), *d_headptr = dev.get<uint64_t>((size_t)n + 1);
+    void *d_tmp = dev.get<char>(cub_bytes);
+    if (!d_istail || !d_tailpos || !d_tailptr || !d_headptr || !d_tmp) return fail(c, HPF_ENOMEM, "set-up arena too small (head split)");
     head_flag_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(c->csr_idx, d_slot, nnz, d_istail);
-    size_t sb = scan_bytes;
+    size_t sb = cub_bytes;
     CU(cub::DeviceScan::ExclusiveSum(d_tmp, sb, (const uint32_t *)d_istail, d_tailpos, (int64_t)(nnz + 1), c->stream));
-    head_split_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, d_y, d_slot, d_tailpos, nnz, c->tail_idx, c->tail_y,
-                                                  head_tile ? hp.idx : nullptr, head_tile ? hp.y : nullptr);
+    head_split_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, d_y, d_slot, d_tailpos, nnz, c->tail_idx, c->tail_y, nullptr, nullptr);
     split_ptr_kernel<<<(n + 256) / 256, 256, 0, c->stream>>>(d_rowptr, d_tailpos, n, d_tailptr, d_headptr);
-    c->launches += 4;
-    CU(cudaMemcpyAsync(h_tailptr, d_tailptr, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (head_tile) TRY(tile_count(c, dev, pin, d_headptr, n, &htc)); // the head is ONE tile: runs = users
-    if (dense_head) {
-      DensePlan &dp = c->dense;
-      dp.ntiles = (n + head::kUsers - 1) / head::kUsers;
-      dp.nhead = H;
-      const size_t n_pad = (size_t)dp.ntiles * head::kUsers;
-      const size_t NB = dp.nblocks;
-      TRY(ensure(c, &dp.Yw, &dp.Yw_cap, NB * n_pad * head::kHead / 4));
-      TRY(ensure(c, &dp.head_ids, &dp.head_ids_cap, NB * head::kHead));
-      TRY(ensure(c, &dp.a_hi, &dp.a_hi_cap, n_pad * head::kFact));
-      TRY(ensure(c, &dp.a_lo, &dp.a_lo_cap, n_pad * head::kFact));
-      TRY(ensure(c, &dp.b_hi, &dp.b_hi_cap, NB * head::kHead * head::kFact));
-      TRY(ensure(c, &dp.b_lo, &dp.b_lo_cap, NB * head::kHead * head::kFact));
-      TRY(ensure(c, &dp.dB_part, &dp.dB_part_cap, NB * std::min<uint32_t>(dp.ntiles, (uint32_t)c->sm_count) * head::kHead * head::kFact));
-      CU(cudaMemsetAsync(dp.Yw, 0, NB * n_pad * head::kHead, c->stream));
-      CU(cudaMemsetAsync(dp.head_ids, 0xff, NB * head::kHead * 4, c->stream));
-      CU(cudaMemcpyAsync(dp.head_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
-      h_yovf = pin.get<uint32_t>(1);
-      if (!h_yovf) return fail(c, HPF_ENOMEM, "pinned arena too small");
-      *h_yovf = 0;
-      CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream)); // free again: stage 1 has read the index check
-      head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, n_pad * head::kHead, dp.Yw, c->scratch_u32);
-      CU(cudaMemcpyAsync(h_yovf, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->launches += 3;
+    DensePlan &dp = c->dense;
+    dp.ntiles = (n + head::kUsers - 1) / head::kUsers;
+    dp.nhead = H;
+    const size_t n_pad = (size_t)dp.ntiles * head::kUsers;
+    const size_t NB = dp.nblocks;
+    TRY(ensure(c, &dp.Yw, &dp.Yw_cap, NB * n_pad * head::kHead / 4));
+    TRY(ensure(c, &dp.head_ids, &dp.head_ids_cap, NB * head::kHead));
+    TRY(ensure(c, &dp.a_hi, &dp.a_hi_cap, n_pad * head::kFact));
+    TRY(ensure(c, &dp.a_lo, &dp.a_lo_cap, n_pad * head::kFact));
+    TRY(ensure(c, &dp.b_hi, &dp.b_hi_cap, NB * head::kHead * head::kFact));
+    TRY(ensure(c, &dp.b_lo, &dp.b_lo_cap, NB * head::kHead * head::kFact));
+    TRY(ensure(c, &dp.dB_part, &dp.dB_part_cap, NB * std::min<uint32_t>(dp.ntiles, (uint32_t)c->sm_count) * head::kHead * head::kFact));
+    CU(cudaMemsetAsync(dp.Yw, 0, NB * n_pad * head::kHead, c->stream));
+    CU(cudaMemsetAsync(dp.head_ids, 0xff, NB * head::kHead * 4, c->stream));
+    CU(cudaMemcpyAsync(dp.head_ids, d_id_s, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    h_yovf = pin.get<uint32_t>(1);
+    if (!h_yovf) return fail(c, HPF_ENOMEM, "pinned arena too small");
+    *h_yovf = 0;
+    head::dense_y_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, c->csr_idx, d_y, d_slot, nnz, n_pad * head::kHead, dp.Yw, c->scratch_u32 + 1);
+    CU(cudaMemcpyAsync(h_yovf, c->scratch_u32 + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->launches++;
+    bool maps_ok = make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) &&
+                   make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers);
+    for (size_t b = 0; b < NB; ++b)
+      maps_ok = maps_ok && make_bf16_map(&dp.map_b_hi[b], dp.b_hi + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead) &&
+                make_bf16_map(&dp.map_b_lo[b], dp.b_lo + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead);
+    if (!maps_ok) return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the dense head operands");
+    // user pass = the tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
+    uint32_t *d_tailrow = nullptr;
+    if (tiles_for(c, m, n, ntail) > 1 && ntail > 0) {
+      d_tailrow = dev.get<uint32_t>(ntail);
+      if (!d_tailrow) return fail(c, HPF_ENOMEM, "set-up arena too small (tail rows)");
+      expand_rows_kernel<<<(unsigned)((ntail + 255) / 256), 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
       c->launches++;
-      bool maps_ok = make_bf16_map(&dp.map_a_hi, dp.a_hi, n_pad, head::kFact, head::kUsers) &&
-                     make_bf16_map(&dp.map_a_lo, dp.a_lo, n_pad, head::kFact, head::kUsers);
-      for (size_t b = 0; b < NB; ++b)
-        maps_ok = maps_ok && make_bf16_map(&dp.map_b_hi[b], dp.b_hi + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead) &&
-                  make_bf16_map(&dp.map_b_lo[b], dp.b_lo + b * head::kHead * head::kFact, head::kHead, head::kFact, head::kHead);
-      if (!maps_ok) return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the dense head operands");
     }
-  }
-  // the item-side host work list (gather mode) can be built while the device works on stage 2
-  if (!item_tile && !try_item_tile) { /* h_run arrived with stage 1 */
-    TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw, skip_ptr));
-  }
-  if (!split_head) { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
-    TRY(orient_device(c, dev, pin, nnz, d_rowof, c->csr_idx, d_y, true, n, m, 0, true, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
+    TRY(orient_device(c, dev, ntail, d_tailrow, c->tail_idx, y ? c->tail_y : nullptr, true, d_tailptr, n, m, &c->upass_idx,
+                      &c->upass_idx_cap, &c->upass_y, &c->upass_y_cap, cub_bytes, &uo));
+    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, ntail, nullptr, 1, uo.d_idx, uo.d_y, cub_bytes, &up));
+  } else { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
+    TRY(orient_device(c, dev, nnz, d_rowof, c->csr_idx, d_y, true, d_rowptr, n, m, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
                       &c->upass_y_cap, cub_bytes, &uo));
-    if (uo.from_host_rowptr) TRY(build_worklist_host(c, pin, n, row_ptr, 1, &uw));
+    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, nnz, nullptr, 1, uo.d_idx, uo.d_y, cub_bytes, &up));
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   tr.mark("stage 2: work lists, split");
-  if (dense_head && h_yovf != nullptr && *h_yovf != 0) {
+  if (*h_bad != 0) return fail(c, HPF_EINVAL, "col_idx holds item %u >= n_items=%u", *h_bad, m);
+  if (dense_head && *h_yovf != 0) {
     // repeated (user, head item) lines whose ratings add up past 255 do not fit a byte of Y (the reference walks every
     // line, hgaprec.cc:1340-1366, so the sum is what counts): plan this input again without the dense head
     const int mode = c->dense_head_mode;
@@ -1386,46 +1283,13 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     c->dense_head_mode = mode;
     return rc;
   }
-
-  // ================= stage 3: remaining host work lists, head work list, uploads =================
-  if (!item_tile && try_item_tile) TRY(build_worklist_host(c, pin, m, io.h_run, io.ntiles, &iw, skip_ptr));
-  if (split_head) {
-    const uint64_t ntail = h_tailptr[n];
-    if (head_tile) {
-      const uint32_t head_nsegs = htc.h_last[0] + htc.h_last[1];
-      TRY(tile_emit(c, c->dev_arena2, d_headptr, htc, n, 1, head_nsegs, &c->head_tile));
-      c->head_tile.on = true; c->head_tile.nnz = nnz - ntail; c->head_tile.tile0_count = H;
-      c->head_tile.has_y = y != nullptr;
-      c->head_tile.cpt = 8u * (uint32_t)c->sm_count;
-    } else {
-      c->dense.on = true;
-      c->dense.a_dirty = true;
-    }
-    // tail: a CSR over the same users (presorted by row); L2-tiled like the plain user pass when needed
-    uint32_t *d_tailrow = nullptr;
-    if (tiles_for(c, m, n, ntail) > 1 && ntail > 0) {
-      d_tailrow = dev.get<uint32_t>(ntail);
-      if (!d_tailrow) return fail(c, HPF_ENOMEM, "set-up arena too small (tail rows)");
-      expand_rows_kernel<<<(unsigned)((ntail + 255) / 256), 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
-      c->launches++;
-    }
-    TRY(orient_device(c, dev, pin, ntail, d_tailrow, c->tail_idx, y ? c->tail_y : nullptr, true, n, m, 0, true, &c->upass_idx,
-                      &c->upass_idx_cap, &c->upass_y, &c->upass_y_cap, cub_bytes, &uo));
-    if (uo.from_host_rowptr) TRY(build_worklist_host(c, pin, n, h_tailptr, 1, &uw));
-    else {
-      CU(cudaStreamSynchronize(c->stream));
-      TRY(build_worklist_host(c, pin, n, uo.h_run, uo.ntiles, &uw));
-    }
-  } else if (!uo.from_host_rowptr) {
-    TRY(build_worklist_host(c, pin, n, uo.h_run, uo.ntiles, &uw));
+  TRY(finish_worklist(c, c->th, up));
+  TRY(finish_worklist(c, c->be, ip));
+  if (dense_head) {
+    c->dense.on = true;
+    c->dense.a_dirty = true;
   }
-  tr.mark("stage 3: host work lists");
-  TRY(upload_worklist(c, c->th, uw, uo.d_idx, uo.d_y));
-  if (!item_tile) TRY(upload_worklist(c, c->be, iw, io.d_idx, io.d_y));
   c->th_tiles = uo.ntiles; c->be_tiles = io.ntiles;
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaGetLastError());
-  tr.mark("uploads");
   c->ratings_set = true;
   return 0;
 }
@@ -1455,6 +1319,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
     c->launches += 4;
     if ((rc = refresh_colsum(c, s))) break;
     s.have_state = true;
+    s.derived_valid = true; // rate and E[v] are the caller's (not functions of shape: src/gpbase.hh:324-340)
     c->aux_dirty = true;
     if (theta_side) c->dense.a_dirty = true;
     if (theta_side) c->th_colsum_global = false;
@@ -1529,6 +1394,10 @@ int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   };
   int rc = 0;
+  if ((which == HPF_THETA || which == HPF_BETA) && (rate || Ev)) {
+    rc = ensure_derived(c, s);
+    if (rc) { cudaFree(stage); return rc; }
+  }
   switch (which) {
   case HPF_THETA:
   case HPF_BETA:
@@ -1567,18 +1436,91 @@ int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev
   return 0;
 }
 
-int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
+// ---- multi-GPU: optimistic handling of the exact fallback (see hpf_ctx::mg_exact) ---------------------------------
+// every array an iteration changes and a later one reads
+void state_arrays(hpf_ctx *c, std::vector<std::pair<void *, size_t>> *v)
 {
-  if (!c) return fail(c, HPF_EINVAL, "null ctx");
-  CU(cudaSetDevice(c->cfg.device));
-  TRY(check_ready(c));
-  TRY(ensure_aux(c));
+  for (int side = 0; side < 2; ++side) {
+    Side &s = side == 0 ? c->th : c->be;
+    const size_t rk = (size_t)s.R * c->ld * sizeof(float), rv = (size_t)s.R * sizeof(float);
+    v->emplace_back(s.A, rk); v->emplace_back(s.Elog, rk); v->emplace_back(s.shape, rk);
+    v->emplace_back(s.shift, rv); v->emplace_back(s.rate_col, c->Kp * sizeof(float));
+    if (c->hier) {
+      v->emplace_back(s.rate_row, rv); v->emplace_back(s.pr_shape, rv); v->emplace_back(s.pr_rate, rv); v->emplace_back(s.pr_Ev, rv);
+      if (c->logl) { v->emplace_back(s.pr_shape_prev, rv); v->emplace_back(s.pr_rate_prev, rv); }
+    }
+    if (c->bias) {
+      v->emplace_back(s.b_shape, rv); v->emplace_back(s.b_rate, rv); v->emplace_back(s.b_Ev, rv); v->emplace_back(s.b_Elog, rv);
+      v->emplace_back(s.aux, (size_t)s.R * sizeof(float2));
+    }
+    v->emplace_back(s.colsum, c->Kp * sizeof(float));
+  }
+  v->emplace_back(c->colsum_theta_old, c->Kp * sizeof(float));
+}
+
+int snapshot_state(hpf_ctx *c, bool restore)
+{
+  std::vector<std::pair<void *, size_t>> v;
+  state_arrays(c, &v);
+  size_t total = 0;
+  for (auto &e : v) total += pad256(e.second);
+  if (!restore) TRY(ensure(c, &c->snap, &c->snap_cap, total / sizeof(float)));
+  char *p = reinterpret_cast<char *>(c->snap);
+  for (auto &e : v) {
+    if (restore) CU(cudaMemcpyAsync(e.first, p, e.second, cudaMemcpyDeviceToDevice, c->stream));
+    else CU(cudaMemcpyAsync(p, e.first, e.second, cudaMemcpyDeviceToDevice, c->stream));
+    p += pad256(e.second);
+  }
+  return 0;
+}
+
+int run_window(hpf_ctx *c, uint32_t n_iters)
+{
   CU(cudaEventRecord(c->ev0, c->stream));
   for (uint32_t it = 0; it < n_iters; ++it) TRY(one_iteration(c));
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
+{
+  if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  CU(cudaSetDevice(c->cfg.device));
+  TRY(check_ready(c));
+  TRY(ensure_aux(c));
+  if (n_iters == 0) return 0;
+  const bool optimistic = c->nranks > 1 && !c->mg_exact;
+  struct Saved { bool th_valid, be_valid, pr_prev_valid, th_global, a_dirty; uint64_t iterations; } sv;
+  if (optimistic) { // keep what a re-run of this window needs
+    sv.th_valid = c->th.derived_valid; sv.be_valid = c->be.derived_valid; sv.pr_prev_valid = c->pr_prev_valid;
+    sv.th_global = c->th_colsum_global; sv.a_dirty = c->dense.a_dirty; sv.iterations = c->iterations;
+    CU(cudaMemsetAsync(c->mg_fired, 0, sizeof(float), c->stream));
+    TRY(snapshot_state(c, false));
+  }
+  TRY(run_window(c, n_iters));
+  if (optimistic) {
+    float fired = 0.f; // all-reduced: the same value on every rank, so every rank takes the same branch
+    CU(cudaMemcpy(&fired, c->mg_fired, sizeof(float), cudaMemcpyDeviceToHost));
+    if (fired != 0.f) {
+      // an item-side nonzero took the exact fallback on some rank: its contribution sits in that rank's Tdirect_beta
+      // only.  Re-run the window from the snapshot with the fallback buffers inside the all-reduce, and stay there.
+      c->mg_exact = true;
+      TRY(snapshot_state(c, true));
+      c->th.derived_valid = sv.th_valid && false; c->be.derived_valid = sv.be_valid && false; // Ev / rate are re-derived on demand
+      c->pr_prev_valid = sv.pr_prev_valid; c->th_colsum_global = sv.th_global; c->iterations = sv.iterations;
+      c->dense.a_dirty = true;
+      const float first_ms = c->last_ms;
+      TRY(run_window(c, n_iters));
+      c->last_ms += first_ms;
+    }
+  }
   return 0;
 }
 
@@ -1590,8 +1532,6 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
   CU(cudaSetDevice(c->cfg.device));
   TRY(check_ready(c));
   TRY(ensure_aux(c));
-  // event order inside one_iteration: 0 user sweep 1 item pass 2 combine 3 user head tile 7 theta 4 all-reduce 5 beta 6
-  static const int seq[8] = { 0, 1, 2, 3, 7, 4, 5, 6 };
   float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
   for (uint32_t it = 0; it < n_iters; ++it) {
     c->profiling = true;
@@ -1599,14 +1539,12 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
     c->profiling = false;
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 8; ++i) {
+      if (i == 3 && !c->dense.on) continue; // stage not run: its events were never recorded
       float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, c->pev[seq[i]], c->pev[seq[i + 1]]));
+      CU(cudaEventElapsedTime(&ms, c->pev[2 * i], c->pev[2 * i + 1]));
       acc[i] += ms;
     }
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, c->pev[0], c->pev[6]));
-    acc[7] += ms;
   }
   CU(cudaGetLastError());
   const float inv = 1.f / (float)n_iters;
@@ -1627,6 +1565,8 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   for (uint64_t p = 0; p < npairs; ++p)
     if (u[p] >= c->th.R || i[p] >= c->be.R) return fail(c, HPF_EINVAL, "pair %llu out of range", (unsigned long long)p);
+  TRY(ensure_derived(c, c->th));
+  TRY(ensure_derived(c, c->be));
   // pairs go through the grow-only set-up arena: no allocation in the steady state
   TRY(arena_reserve(c, c->dev_arena, 2 * pad256(npairs * 4) + pad256(npairs) + 4096));
   uint32_t *du = c->dev_arena.get<uint32_t>(npairs), *di = c->dev_arena.get<uint32_t>(npairs);
@@ -1665,6 +1605,8 @@ int hpf_elbo(hpf_ctx *c, double *elbo_out)
     return fail(c, HPF_EINVAL, "hpf_elbo with HPF_HIER needs at least one hpf_iterate since THETARATE/BETARATE were set "
                                "(logl() uses the rate priors of the last iteration, gpbase.hh:163-173)");
   CU(cudaSetDevice(c->cfg.device));
+  TRY(ensure_derived(c, c->th));
+  TRY(ensure_derived(c, c->be));
   const uint32_t per = (uint32_t)c->sm_count * 8u; // partial sums per launch
   CU(cudaMemsetAsync(c->elbo_blocks, 0, sizeof(double) * kElboLaunches * per, c->stream));
   uint32_t slot = 0;
@@ -1736,6 +1678,8 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
   CU(cudaSetDevice(c->cfg.device));
+  TRY(ensure_derived(c, c->th));
+  TRY(ensure_derived(c, c->be));
   const uint32_t n = c->th.R, m = c->be.R;
   for (uint32_t a = 0; a < nu; ++a)
     if (users[a] >= n) return fail(c, HPF_EINVAL, "users[%u]=%u >= n_users=%u", a, users[a], n);
@@ -1842,6 +1786,8 @@ int hpf_item_ranks(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
   CU(cudaSetDevice(c->cfg.device));
+  TRY(ensure_derived(c, c->th));
+  TRY(ensure_derived(c, c->be));
   const uint32_t n = c->th.R, m = c->be.R;
   for (uint32_t a = 0; a < nu; ++a)
     if (users[a] >= n) return fail(c, HPF_EINVAL, "users[%u]=%u >= n_users=%u", a, users[a], n);
@@ -1944,12 +1890,13 @@ int hpf_comm_init(hpf_ctx *c, int rank, int nranks, const void *id, size_t id_by
   int rc = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
   if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   c->rank = rank; c->nranks = nranks;
-  if (const char *e = getenv("HPF_AR_OVERLAP")) c->ar_overlap = atoi(e) != 0 && nranks > 1;
-  if (c->ar_overlap && !c->comm_stream) {
+  if (nranks > 1 && !c->comm_stream) {
     CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ev_tbeta, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_ar, cudaEventDisableTiming));
+    for (auto &e : c->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_theta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
   }
+  // ratings planned before the communicator existed have one chunk: still correct, the all-reduce just overlaps less
   return 0;
 }
 
@@ -1969,10 +1916,12 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
   out->sweep_group = c->sweep_g;
   out->sweep_vec = c->sweep_v;
   out->last_topn_ms = c->last_topn_ms;
-  out->tile_rows = c->tile_rows;
-  out->item_tiles = c->item_tile.on ? c->item_tile.ntiles : 0;
-  out->head_nnz = c->head_tile.on ? c->head_tile.nnz : (c->dense.on ? c->dense.head_nnz : 0);
-  out->tile_segments = (uint64_t)(c->item_tile.on ? c->item_tile.nsegs : 0) + (c->head_tile.on ? c->head_tile.nsegs : 0);
+  out->user_l2_tiles = c->th_tiles;
+  out->item_l2_tiles = c->be_tiles;
+  out->head_nnz = c->dense.on ? c->dense.head_nnz : 0;
+  out->item_chunks = c->be.wl.nchunks;
+  out->mg_exact = c->mg_exact ? 1u : 0u;
+  out->n_devices = 1;
   return 0;
 }
 

@@ -314,215 +314,6 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
   }
 }
 
-// ---------------------------------------------------------------------------
-// K1b: tile sweep.  Same arithmetic as sweep_kernel, but the GATHERED factor rows
-// come from shared memory: a tile of up to tile_rows rows of the column side is
-// staged once per CTA (packed K floats per row) and every nonzero whose column
-// falls into that tile reads it from there -- the L2->SM gather, which bounds
-// sweep_kernel, disappears.  Two uses:
-//   item pass   rows = items, tiles = consecutive blocks of users; an item's
-//               nonzeros inside one user block form one segment;
-//   user pass   rows = users, ONE tile holding the most popular items (a Zipf
-//               head carries most of the nonzeros); the tail stays in sweep_kernel.
-// A row's sum is spread over many CTAs, so partial sums are added to T with
-// vector reductions (red.global.add.v4.f32) -- T is cleared (item pass) or
-// written by sweep_kernel (user pass) beforehand on the same stream.
-// Work: chunk c = (tile c / cpt, part c % cpt) covers an even share of the
-// tile's segments (tile_seg_ptr); CTAs take chunks round-robin.
-// ---------------------------------------------------------------------------
-#ifndef HPF_TILE_THREADS
-#define HPF_TILE_THREADS 640
-#endif
-constexpr int kTileThreads = HPF_TILE_THREADS;
-
-struct TileArgs {
-  const uint4 *seg;             // {begin_lo, begin_hi, row, len}, sorted by (tile, len desc)
-  const uint32_t *tile_seg_ptr; // [ntiles + 1]
-  uint32_t ntiles, cpt;         // chunks per tile
-  uint32_t tile_rows;           // rows per tile (last tile may hold fewer)
-  uint32_t C;                   // rows on the column side
-  const uint32_t *tile_row_ids; // explicit row list of tile 0 (single-tile use) or nullptr: tile t = rows [t*tile_rows, ...)
-  uint32_t tile0_count;         // rows in the explicit list
-  const uint32_t *idx;          // per nonzero: SLOT inside its tile
-  const uint8_t *y;
-  const float *Arow, *Acol;     // [. x ld]
-  float *T;                     // [R x ld]  +=
-  const float2 *row_aux, *col_aux;
-  float *Tb;                    // [R] +=
-  const float *ElogRow, *ElogCol, *ElogbRow, *ElogbCol;
-  float *Tdirect, *Tbdirect;
-  uint32_t *direct_flag;
-  unsigned long long *slow_count;
-  uint32_t K, K4, ld, ld4;
-};
-
-__device__ __forceinline__ void red_add_v4(float *addr, float4 v)
-{
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-template <int G, int V, bool BIAS>
-__global__ void __launch_bounds__(kTileThreads, 1) tile_sweep_kernel(const TileArgs a)
-{
-  extern __shared__ float4 tile_sm[]; // [tile_rows x K4] (+ float2 aux[tile_rows] with BIAS)
-  float2 *aux_sm = reinterpret_cast<float2 *>(tile_sm + (size_t)a.tile_rows * a.K4);
-  const int lane = threadIdx.x & 31;
-  const int gl = lane & (G - 1);
-  const uint32_t gid = threadIdx.x / G;              // group inside the CTA
-  constexpr uint32_t kGroups = kTileThreads / G;
-  const uint32_t nchunks = a.ntiles * a.cpt;
-  uint32_t cur_tile = 0xffffffffu;
-  bool pq[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) pq[v] = (uint32_t)(gl + v * G) < a.K4;
-  // lanes past the last float4 of a row re-read it (row-side value 0, sums never stored): only the last slot can be
-  const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
-
-  for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const uint32_t tile = ch / a.cpt, part = ch % a.cpt;
-    // the tile's segments are sorted by length: part p takes every cpt-th one, so the parts carry equal work
-    const uint32_t t0 = __ldg(a.tile_seg_ptr + tile), t1 = __ldg(a.tile_seg_ptr + tile + 1);
-    if (t0 + part >= t1) continue;
-    const uint32_t nmine = (t1 - t0 - part + a.cpt - 1) / a.cpt; // segments t0 + part + cpt * i, i < nmine
-    const uint32_t tile_base = tile * a.tile_rows;
-    if (tile != cur_tile) { // stage the tile's factor rows (and bias terms)
-      __syncthreads();
-      const uint32_t nrows = a.tile_row_ids ? a.tile0_count : min(a.tile_rows, a.C - tile_base);
-      const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
-      for (uint32_t e = threadIdx.x; e < nrows * a.K4; e += kTileThreads) {
-        const uint32_t r = e / a.K4, q = e - r * a.K4;
-        const uint32_t src = a.tile_row_ids ? __ldg(a.tile_row_ids + r) : tile_base + r;
-        tile_sm[e] = __ldg(acol + (size_t)src * a.ld4 + q);
-      }
-      if (BIAS)
-        for (uint32_t r = threadIdx.x; r < nrows; r += kTileThreads)
-          aux_sm[r] = __ldg(a.col_aux + (a.tile_row_ids ? __ldg(a.tile_row_ids + r) : tile_base + r));
-      cur_tile = tile;
-      __syncthreads();
-    }
-    // the 32/G groups of a warp advance in lock-step over consecutive (equally long) segments
-    for (uint32_t ib = gid & ~(uint32_t)(32 / G - 1); ib < nmine; ib += kGroups) {
-      const uint32_t i = ib + (gid & (32 / G - 1));
-      const bool have = i < nmine;
-      const uint32_t sidx = t0 + part + a.cpt * i;
-      uint64_t begin = 0;
-      uint32_t row = 0, len = 0;
-      if (have) {
-        const uint4 s = __ldg(a.seg + sidx);
-        begin = (uint64_t)s.x | ((uint64_t)s.y << 32);
-        row = s.z;
-        len = s.w;
-      }
-      float4 ar[V], acc[V], b[V];
-      {
-        const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.ld4;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          ar[v] = (have && pq[v]) ? ldg4(rp + gl + v * G) : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          b[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      float2 raux = make_float2(0.f, 0.f);
-      float accb = 0.f;
-      if (BIAS && have) raux = __ldg(a.row_aux + row);
-      const uint32_t maxlen = __reduce_max_sync(0xffffffffu, len);
-      const uint32_t *ip = a.idx + begin;
-      const uint8_t *yp = a.y ? a.y + begin : nullptr;
-      for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
-        const uint32_t jj = j0 + gl;
-        const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // slot 0 past the end: valid
-        const float ybuf = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f;
-        HPF_UNROLL(HPF_UNROLL_T)
-        for (int t = 0; t < G; ++t) {
-          const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
-          const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
-          const float4 *cp = tile_sm + (size_t)c * a.K4;
-#pragma unroll
-          for (int v = 0; v < V - 1; ++v) b[v] = cp[gl + v * G];
-          b[V - 1] = cp[q_last];
-          float dot = dot_rows<V>(ar, b);
-#pragma unroll
-          for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-          float z = dot;
-          float2 caux = make_float2(0.f, 0.f);
-          if (BIAS) {
-            caux = aux_sm[c];
-            z += raux.x * caux.y + caux.x * raux.y;
-          }
-          const bool ok = z > kZMin && z < kZMax;
-          const float sc = ok ? yv * frcp(z) : 0.f;
-          axpy_rows<V>(sc, b, acc);
-          if (BIAS) accb = fmaf(sc, caux.y, accb);
-          if (!ok && yv != 0.f) { // Z left the fp32 range: exact log-domain path (rare)
-            SlowArgs sa;
-            sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
-            sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
-            sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
-            const uint32_t cg = a.tile_row_ids ? __ldg(a.tile_row_ids + c) : tile_base + c;
-            sweep_slow_path<G, V, BIAS>(sa, row, cg, yv, lane);
-          }
-        }
-      }
-      if (have && len > 0) {
-        float *dst = a.T + (size_t)row * a.ld;
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (pq[v]) red_add_v4(dst + (size_t)(gl + v * G) * 4, acc[v]);
-        if (BIAS && gl == 0) atomicAdd(a.Tb + row, accb);
-      }
-    }
-  }
-}
-
-// ---- device-side work list of the tile sweep ----------------------------------
-// run q = tile * R + row covers nonzeros [run_ptr[q], run_ptr[q+1]); it is cut into
-// segments of <= L nonzeros.  cnt[q] = segments of run q.
-__global__ void seg_count_kernel(const uint64_t *run_ptr, uint64_t nruns, uint32_t L, uint32_t *cnt)
-{
-  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < nruns) {
-    const uint64_t len = run_ptr[q + 1] - run_ptr[q];
-    cnt[q] = (uint32_t)((len + L - 1) / L);
-  }
-}
-
-// segments of run q go to slots [off[q], off[q] + cnt); key orders them by (tile, descending length)
-__global__ void seg_emit_kernel(const uint64_t *run_ptr, const uint32_t *off, uint64_t nruns, uint32_t R, uint32_t L,
-                                uint4 *seg, uint32_t *key)
-{
-  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nruns) return;
-  const uint64_t b0 = run_ptr[q], len = run_ptr[q + 1] - b0;
-  if (len == 0) return;
-  const uint32_t tile = (uint32_t)(q / R), row = (uint32_t)(q % R);
-  const uint32_t cnt = (uint32_t)((len + L - 1) / L);
-  uint32_t o = off[q];
-  for (uint32_t s = 0; s < cnt; ++s, ++o) {
-    const uint64_t sb = b0 + (uint64_t)s * L;
-    const uint32_t sl = (uint32_t)min((uint64_t)L, len - (uint64_t)s * L);
-    seg[o] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), row, sl);
-    key[o] = tile * (L + 1) + (L - sl);
-  }
-}
-
-// tile_ptr[t] = first sorted segment whose tile is >= t, t in [0, ntiles]
-__global__ void tile_ptr_kernel(const uint32_t *sorted_key, uint32_t nsegs, uint32_t Lp1, uint32_t ntiles, uint32_t *tile_ptr)
-{
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > nsegs) return;
-  const uint32_t prev = j == 0 ? 0u : sorted_key[j - 1] / Lp1 + 1u;
-  const uint32_t cur = j == nsegs ? ntiles + 1u : sorted_key[j] / Lp1 + 1u;
-  for (uint32_t t = prev; t < cur && t <= ntiles; ++t) tile_ptr[t] = j;
-}
-
-// column-side index -> slot inside its tile of tile_rows consecutive rows
-__global__ void to_slot_kernel(uint32_t *idx, uint64_t nnz, uint32_t tile_rows)
-{
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < nnz) idx[j] %= tile_rows;
-}
-
 // ---- head / tail split of the user pass ----------------------------------------
 // item degrees from the item-pass runs (run q = tile * R + item): no atomics on the hot items
 __global__ void degree_kernel(const uint64_t *run_ptr, uint32_t R, uint32_t ntiles, uint32_t *deg)
@@ -633,22 +424,35 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const Combin
 }
 
 // ---------------------------------------------------------------------------
-// K2/K3/K4/K5: dense row update, one warp per row.  Fuses, for one parameter
-// matrix: shape = prior + A*T (the add_slice sums), rate (set_prior_rate +
+// K2/K3/K4/K5: dense row update, one warp per row, 128-bit accesses (lane l owns
+// float4 #(l + 32 v), v < V, of the row).  Fuses, for one parameter matrix:
+// shape = prior + A*T (the add_slice sums), rate (set_prior_rate +
 // update_rate_next, gpbase.hh:163-173,218-223 / GR 560-564), swap (240-246),
 // compute_expectations (248-262), sum_rows / sum_cols (264-280), the GPArray
 // xi/eta step (hgaprec.cc:1398-1414, gpbase.hh:877-925), the bias step
 // (hgaprec.cc:1388-1396) and the next iteration's shifted exponentials.
+//
+// Per iteration only what the NEXT iteration reads is stored: A (sweep operand),
+// Elog (exact fallback) and shape.  The rate is rank-2 structured -- rate_uk =
+// E[xi_u] + sum_i E[beta_ik] (hier) or a K-vector (GR) -- so the kernel keeps its
+// two terms (rate_row[r], rate_col[k]) instead of an R x K matrix,
+// and E[v] = shape / rate is only needed by the report-window consumers
+// (held-out ll, top-N, ELBO, hpf_get_state): derive_kernel materialises rate and
+// E[v] from shape and the two terms on demand, with the same fp32 operations, so
+// the values are the ones this kernel used for its row / column sums.
 // ---------------------------------------------------------------------------
 struct UpdateArgs {
-  uint32_t R, K, Kp, ld; // Kp: K rounded up to 4; ld: row stride in floats
-  const float *T;
-  float *Tdirect;
+  uint32_t R, K, Kp, K4, ld4; // Kp: K rounded up to 4; K4 = Kp / 4; ld4: row stride in float4
+  const float4 *T;
+  float4 *Tdirect;
   const uint32_t *direct_flag;
-  float *A, *Elog, *Ev, *shape, *rate; // rate: [R x ld] (hier) or [Kp] (global rate)
+  const float *direct_flag_all;        // multi-GPU exact mode: the all-reduced item-side flag (or nullptr)
+  float4 *A, *Elog, *shape;
   float *shift;                        // [R]
   int hier;
-  const float *colsum_other; // [Kp]  sum over the OTHER side's rows of Ev
+  const float *colsum_other;           // [Kp]  sum over the OTHER side's rows of Ev
+  float *rate_vec;                     // [Kp]  GR: the rate vector (written by block 0); hier: unused
+  float *rate_row;                     // [R]   hier: the E[xi] / E[eta] this update used
   float prior_shape, prior_rate;
   float *pr_shape, *pr_rate, *pr_Ev;   // GPArray xi / eta (hier)
   float pr_prior_shape, pr_prior_rate;
@@ -679,63 +483,121 @@ __device__ __forceinline__ float warp_max(float v)
 
 __device__ __forceinline__ float floor30(float v) { return v > 0.f ? v : 1e-30f; } // make_nonzero, gpbase.hh:27-44
 
-__global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateArgs a)
+__device__ __forceinline__ float &f4at(float4 &v, int j) { return reinterpret_cast<float *>(&v)[j]; }
+__device__ __forceinline__ float f4get(const float4 &v, int j) { return reinterpret_cast<const float *>(&v)[j]; }
+
+// resident blocks the register budget is set for: V float4 per lane of row operands, twice (two rows in flight)
+constexpr int update_min_blocks(int V) { return V <= 2 ? 3 : (V <= 4 ? 2 : 1); }
+
+template <int V>
+__global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) update_kernel(const UpdateArgs a)
 {
   extern __shared__ float cs[]; // [kUpdateWarps][Kp] column partial sums of Ev
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *mycs = cs + (size_t)w * a.Kp;
-  for (uint32_t k = lane; k < a.Kp; k += 32) mycs[k] = 0.f;
-  const bool use_direct = *a.direct_flag != 0u;
+  const bool use_direct = *a.direct_flag != 0u || (a.direct_flag_all != nullptr && *a.direct_flag_all != 0.f);
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
 
   // the global-rate (GPMatrixGR) vector is written once, by block 0
   if (!a.hier && blockIdx.x == 0)
     for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x)
-      a.rate[k] = k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f;
+      a.rate_vec[k] = k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f;
 
-  for (uint32_t r = blockIdx.x * kUpdateWarps + w; r < a.R; r += warps_total) {
-    const size_t base = (size_t)r * a.ld;
+  // this lane's columns: the rate's column term and the running column sums stay in registers
+  float4 cterm[V], csum[V];
+  bool act[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint32_t q = lane + 32 * v;
+    act[v] = q < a.K4;
+    csum[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cterm[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act[v]) cterm[v] = __ldg(reinterpret_cast<const float4 *>(a.colsum_other) + q);
+  }
+
+  uint32_t r = blockIdx.x * kUpdateWarps + w;
+  float4 av[V], tv[V];
+  if (r < a.R) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (act[v]) {
+        av[v] = a.A[(size_t)r * a.ld4 + lane + 32 * v];
+        tv[v] = __ldg(a.T + (size_t)r * a.ld4 + lane + 32 * v);
+      }
+  }
+  for (; r < a.R; r += warps_total) {
+    const size_t base = (size_t)r * a.ld4;
+    // the next row's operands are requested before this row's arithmetic (two rows in flight per warp)
+    const uint32_t rn = r + warps_total;
+    float4 an[V], tn[V];
+    if (rn < a.R) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (act[v]) {
+          an[v] = a.A[(size_t)rn * a.ld4 + lane + 32 * v];
+          tn[v] = __ldg(a.T + (size_t)rn * a.ld4 + lane + 32 * v);
+        }
+    }
     const float rprior = a.hier ? a.pr_Ev[r] : a.prior_rate;
     float mx = -CUDART_INF_F, rowsum = 0.f;
-    for (uint32_t k = lane; k < a.Kp; k += 32) {
-      if (k < a.K) {
-        float s = a.prior_shape + a.A[base + k] * a.T[base + k];
-        if (use_direct) {
-          s += a.Tdirect[base + k];
-          a.Tdirect[base + k] = 0.f;
-        }
-        const float rt = rprior + a.colsum_other[k];
-        const float sa = floor30(s), rb = floor30(rt);
-        const float ev = sa / rb;
-        const float el = digammaf(sa) - logf(rb);
-        a.shape[base + k] = s;
-        if (a.hier) a.rate[base + k] = rt;
-        a.Ev[base + k] = ev;
-        a.Elog[base + k] = el;
-        mx = fmaxf(mx, el);
-        rowsum += ev;
-        mycs[k] += ev;
-      } else {
-        a.shape[base + k] = 0.f;
-        if (a.hier) a.rate[base + k] = 1.f;
-        a.Ev[base + k] = 0.f;
-        a.Elog[base + k] = -CUDART_INF_F;
+    float4 el[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (!act[v]) continue;
+      const uint32_t q = lane + 32 * v;
+      float4 sh;
+      float4 td = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (use_direct) {
+        td = a.Tdirect[base + q];
+        a.Tdirect[base + q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (q * 4 + j < a.K) {
+          float s = a.prior_shape + f4get(av[v], j) * f4get(tv[v], j);
+          if (use_direct) s += f4get(td, j);
+          const float rt = rprior + f4get(cterm[v], j);
+          const float sa = floor30(s), rb = floor30(rt);
+          const float ev = sa / rb;
+          const float e = digammaf(sa) - logf(rb);
+          f4at(sh, j) = s;
+          f4at(el[v], j) = e;
+          mx = fmaxf(mx, e);
+          rowsum += ev;
+          f4at(csum[v], j) += ev;
+        } else {
+          f4at(sh, j) = 0.f;
+          f4at(el[v], j) = -CUDART_INF_F;
+        }
+      }
+      a.shape[base + q] = sh;
+      a.Elog[base + q] = el[v];
     }
     mx = warp_max(mx);
     rowsum = warp_sum(rowsum);
-    for (uint32_t k = lane; k < a.Kp; k += 32) {
-      const float av = k < a.K ? expf(a.Elog[base + k] - mx) : 0.f;
-      a.A[base + k] = av;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (!act[v]) continue;
+      const uint32_t q = lane + 32 * v;
+      float4 an4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f4at(an4, j) = q * 4 + j < a.K ? expf(f4get(el[v], j) - mx) : 0.f;
+      a.A[base + q] = an4;
       if (a.split_hi != nullptr) { // x = hi + lo in bf16 (representation error 2^-18)
-        const __nv_bfloat16 h = __float2bfloat16_rn(av);
-        a.split_hi[(size_t)r * a.split_ld + k] = h;
-        a.split_lo[(size_t)r * a.split_ld + k] = __float2bfloat16_rn(av - __bfloat162float(h));
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = __float2bfloat16_rn(f4get(an4, j));
+          l[j] = __float2bfloat16_rn(f4get(an4, j) - __bfloat162float(h[j]));
+        }
+        const size_t o = (size_t)r * a.split_ld + (size_t)q * 4;
+        *reinterpret_cast<uint2 *>(a.split_hi + o) = *reinterpret_cast<const uint2 *>(h);
+        *reinterpret_cast<uint2 *>(a.split_lo + o) = *reinterpret_cast<const uint2 *>(l);
       }
     }
     if (lane == 0) {
       a.shift[r] = mx;
       if (a.hier) {
+        a.rate_row[r] = rprior;
         // hgaprec.cc:1399-1405: shape = a' + K a', rate = b' + sum_k E[theta_uk]
         const float ps = a.pr_prior_shape + (float)a.K * a.pr_prior_shape;
         const float pr = a.pr_prior_rate + rowsum;
@@ -767,7 +629,13 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
         }
       }
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) { av[v] = an[v]; tv[v] = tn[v]; }
   }
+  // block partial of the column sums: warps in a fixed order
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+    if (act[v]) reinterpret_cast<float4 *>(cs + (size_t)w * a.Kp)[lane + 32 * v] = csum[v];
   __syncthreads();
   float *dst = a.colsum_partial + (size_t)blockIdx.x * a.Kp;
   for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x) {
@@ -778,11 +646,51 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) update_kernel(const UpdateA
   }
 }
 
+// rate and E[v] of a parameter matrix from its shape and the two rate terms the last update used
+// (report-window consumers only; see update_kernel).  One thread per float4.
+struct DeriveArgs {
+  uint32_t R, K, K4, ld4;
+  const float4 *shape;
+  float4 *Ev, *rate;        // rate: [R x ld] (hier) or nullptr
+  int hier;
+  const float *rate_row;    // [R]   hier
+  const float *rate_col;    // [Kp]  hier: the column sums the update used; GR: the rate vector
+};
+__global__ void __launch_bounds__(256) derive_kernel(const DeriveArgs a)
+{
+  const uint64_t total = (uint64_t)a.R * a.K4;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(e / a.K4), q = (uint32_t)(e - (uint64_t)r * a.K4);
+    const size_t o = (size_t)r * a.ld4 + q;
+    const float4 sh = a.shape[o];
+    const float4 ct = __ldg(reinterpret_cast<const float4 *>(a.rate_col) + q);
+    const float rr = a.hier ? __ldg(a.rate_row + r) : 0.f;
+    float4 ev, rt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (q * 4 + j < a.K) {
+        const float t = a.hier ? rr + f4get(ct, j) : f4get(ct, j);
+        f4at(rt, j) = t;
+        f4at(ev, j) = floor30(f4get(sh, j)) / floor30(t);
+      } else {
+        f4at(rt, j) = 1.f;
+        f4at(ev, j) = 0.f;
+      }
+    }
+    a.Ev[o] = ev;
+    if (a.rate != nullptr) a.rate[o] = rt;
+  }
+}
+
 // colsum[k] = sum over blocks of partial[b][k], accumulated in double in a fixed
 // order (one block per 32 columns, 8 row groups per block); also clears the side's
-// direct_flag for the next iteration.
+// direct_flag for the next iteration.  Multi-GPU bookkeeping of the exact fallback
+// (one thread): flag_out[0] = 1.0 if *flag_in is set (the theta update publishes the
+// ITEM side's flag into the tail of the reduce block), sticky[0] += reduced[0] (the
+// beta update accumulates the all-reduced flag; read by hpf_iterate at its end).
 __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
-                                                             float *colsum, uint32_t *direct_flag)
+                                                             float *colsum, uint32_t *direct_flag, const uint32_t *flag_in,
+                                                             float *flag_out, const float *reduced, float *sticky)
 {
   __shared__ double part[8][32];
   const uint32_t kx = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -798,7 +706,11 @@ __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *parti
     for (int q = 0; q < 8; ++q) t += part[q][kx];
     colsum[k] = (float)t;
   }
-  if (direct_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *direct_flag = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (flag_out != nullptr) flag_out[0] = *flag_in != 0u ? 1.f : 0.f;
+    if (sticky != nullptr) sticky[0] += reduced[0];
+    if (direct_flag != nullptr) *direct_flag = 0u;
+  }
 }
 
 // column sums of an existing Ev matrix (after hpf_set_state)
@@ -997,26 +909,25 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n)
   if (j < n) p[j] = (uint32_t)j;
 }
 
-// key[j] = src[perm[j]] / div   (div == 1: plain gather)
-__global__ void gather_key_kernel(const uint32_t *perm, const uint32_t *src, uint32_t div, uint64_t nnz, uint32_t *key)
-{
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < nnz) key[j] = src[perm[j]] / div;
-}
-
-// apply the final permutation: gathered-side index, rating, and the composite
-// key tile * R + row that the run pointers are derived from
-__global__ void apply_perm_kernel(const uint32_t *perm, const uint32_t *row, const uint32_t *col, const uint8_t *y,
-                                  uint32_t tile_cols, uint32_t R, uint64_t nnz, uint32_t *out_idx, uint8_t *out_y,
-                                  uint32_t *out_key)
+// sort key and payload of one nonzero for an orientation: key = tile(col) * R + row, payload = col | y << 32.
+// One stable radix sort of (key, payload) orders the nonzeros by (tile, row) and carries the gathered-side
+// index and the rating along -- no permutation to chase afterwards.
+__global__ void orient_key_kernel(const uint32_t *row, const uint32_t *col, const uint8_t *y, uint32_t tile_cols, uint32_t R,
+                                  uint64_t nnz, uint32_t *key, uint64_t *val)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
-  const uint32_t p = perm[j];
-  const uint32_t cc = col[p];
-  out_idx[j] = cc;
-  if (y != nullptr) out_y[j] = y[p];
-  out_key[j] = (cc / tile_cols) * R + row[p];
+  const uint32_t cc = col[j];
+  key[j] = (cc / tile_cols) * R + row[j];
+  val[j] = (uint64_t)cc | ((uint64_t)(y != nullptr ? y[j] : 1u) << 32);
+}
+__global__ void orient_unpack_kernel(const uint64_t *val, uint64_t nnz, uint32_t *out_idx, uint8_t *out_y)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const uint64_t v = val[j];
+  out_idx[j] = (uint32_t)v;
+  if (out_y != nullptr) out_y[j] = (uint8_t)(v >> 32);
 }
 
 // run_ptr[c] = first position whose sorted key is >= c, for c in [0, nkeys]
@@ -1027,6 +938,130 @@ __global__ void run_ptr_kernel(const uint32_t *sorted_key, uint64_t nnz, uint32_
   const uint32_t prev = j == 0 ? 0u : sorted_key[j - 1] + 1u;
   const uint32_t cur = j == nnz ? nkeys + 1u : sorted_key[j] + 1u;
   for (uint32_t c = prev; c < cur && c <= nkeys; ++c) run_ptr[c] = j;
+}
+
+// ---------------------------------------------------------------------------
+// work lists, built on the device.  The nonzeros of one orientation arrive as
+// RUNS: run (t, r) holds the nonzeros of row r whose gathered-side index lies in
+// L2 tile t; run_ptr[t * R + r] is where it starts (ntiles == 1: the plain row
+// pointer).  Every run is cut into segments of <= L nonzeros -- the unit one
+// group of sweep_kernel lanes owns.  A row with one segment writes its T row
+// itself; a row with several writes partial slots that combine_kernel adds in a
+// fixed order.  A row without nonzeros gets one empty segment (it clears its T
+// row); a skipped row (head item of the dense-head plan) gets none.  Segments are
+// ordered by (chunk of rows, tile, descending length): blocks are scheduled in
+// index order, so a launch walks one tile's L2-resident factor rows at a time,
+// the 32/G segments a warp advances in lock-step have equal trip counts, and long
+// work starts first.  CHUNKS are equal ranges of rows that are launched one after
+// the other, so that the all-reduce of a finished chunk's T rows can run under the
+// next chunk's sweep (multi-GPU; one chunk otherwise).
+// ---------------------------------------------------------------------------
+struct WlArgs {
+  const uint64_t *run_ptr;   // [ntiles * R + 1]
+  uint32_t R, ntiles, L;
+  uint32_t chunk_rows;       // rows per chunk
+  const uint32_t *skip_slot; // [R] != 0xffffffff: the row is skipped; or nullptr
+  uint32_t *segcnt, *multicnt, *ismulti; // [R] counts (phase 1), then their exclusive scans in *_off
+  uint32_t *seg_off, *first_off, *multi_off;
+  uint4 *seg_u;              // unsorted segments {begin_lo, begin_hi, row, len}
+  uint32_t *out_u, *key_u;   // unsorted output slot, sort key
+  uint32_t *multi_row, *multi_first, *multi_cnt;
+};
+
+__global__ void wl_count_kernel(const WlArgs a)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  uint32_t cnt = 0;
+  if (a.skip_slot == nullptr || a.skip_slot[r] == 0xffffffffu) {
+    for (uint32_t t = 0; t < a.ntiles; ++t) {
+      const size_t q = (size_t)t * a.R + r;
+      const uint64_t len = a.run_ptr[q + 1] - a.run_ptr[q];
+      cnt += (uint32_t)((len + a.L - 1) / a.L);
+    }
+    if (cnt == 0) cnt = 1; // the empty segment that clears the row's T
+  }
+  a.segcnt[r] = cnt;
+  a.multicnt[r] = cnt > 1 ? cnt : 0u;
+  a.ismulti[r] = cnt > 1 ? 1u : 0u;
+}
+
+__global__ void wl_emit_kernel(const WlArgs a)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  const uint32_t cnt = a.segcnt[r];
+  if (cnt == 0) return;
+  const uint32_t chunk = r / a.chunk_rows;
+  uint32_t o = a.seg_off[r], j = 0;
+  const uint32_t first = a.first_off[r];
+  if (cnt > 1) {
+    const uint32_t mp = a.multi_off[r];
+    a.multi_row[mp] = r; a.multi_first[mp] = first; a.multi_cnt[mp] = cnt;
+  }
+  for (uint32_t t = 0; t < a.ntiles; ++t) {
+    const size_t q = (size_t)t * a.R + r;
+    const uint64_t b0 = a.run_ptr[q], len = a.run_ptr[q + 1] - b0;
+    const uint32_t n = (uint32_t)((len + a.L - 1) / a.L);
+    for (uint32_t s = 0; s < n; ++s, ++o, ++j) {
+      const uint64_t sb = b0 + (uint64_t)s * a.L;
+      const uint32_t sl = (uint32_t)min((uint64_t)a.L, len - (uint64_t)s * a.L);
+      a.seg_u[o] = make_uint4((uint32_t)sb, (uint32_t)(sb >> 32), r, sl);
+      a.out_u[o] = cnt == 1 ? r : a.R + first + j;
+      a.key_u[o] = (chunk * a.ntiles + t) * (a.L + 1) + (a.L - sl);
+    }
+  }
+  if (j == 0) { // no nonzeros at all: one empty segment in tile 0
+    const uint64_t b0 = a.run_ptr[r];
+    a.seg_u[o] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), r, 0u);
+    a.out_u[o] = r;
+    a.key_u[o] = (chunk * a.ntiles) * (a.L + 1) + a.L;
+  }
+}
+
+// apply the sort: seg[j] = seg_u[perm[j]], seg_out[j] = out_u[perm[j]]
+__global__ void wl_gather_kernel(const uint32_t *perm, const uint4 *seg_u, const uint32_t *out_u, const uint32_t *total,
+                                 uint4 *seg, uint32_t *seg_out)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *total) return;
+  const uint32_t p = perm[j];
+  seg[j] = seg_u[p];
+  seg_out[j] = out_u[p];
+}
+
+// totals and chunk boundaries -> info: {nsegs, nslots, nmulti, 0, seg bound[0..nchunks], multi bound[0..nchunks]}
+__global__ void wl_info_kernel(const WlArgs a, const uint32_t *sorted_key, uint32_t nchunks, uint32_t *info)
+{
+  if (blockIdx.x != 0) return;
+  __shared__ uint32_t tot[3];
+  if (threadIdx.x == 0) {
+    const uint32_t l = a.R - 1;
+    tot[0] = a.seg_off[l] + a.segcnt[l];
+    tot[1] = a.first_off[l] + a.multicnt[l];
+    tot[2] = a.multi_off[l] + a.ismulti[l];
+    info[0] = tot[0]; info[1] = tot[1]; info[2] = tot[2]; info[3] = 0;
+  }
+  __syncthreads();
+  const uint32_t nsegs = tot[0], nmulti = tot[2];
+  for (uint32_t c = threadIdx.x; c <= nchunks; c += blockDim.x) {
+    // first sorted segment whose key belongs to chunk >= c
+    const uint64_t want = (uint64_t)c * a.ntiles * (a.L + 1);
+    uint32_t lo = 0, hi = nsegs;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if ((uint64_t)sorted_key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    info[4 + c] = c == nchunks ? nsegs : lo;
+    // first multi-segment row >= c * chunk_rows (multi_row is ascending)
+    const uint64_t wrow = (uint64_t)c * a.chunk_rows;
+    lo = 0; hi = nmulti;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if ((uint64_t)a.multi_row[mid] < wrow) lo = mid + 1; else hi = mid;
+    }
+    info[4 + nchunks + 1 + c] = c == nchunks ? nmulti : lo;
+  }
 }
 
 // any index >= limit?  (argument check of hpf_set_ratings_csr, done on the device)

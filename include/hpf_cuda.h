@@ -103,12 +103,17 @@ typedef struct hpf_stats {
                                 on the library's own stream)                       */
   uint32_t sweep_group;      /* lanes cooperating on one nonzero in the sweep      */
   uint32_t sweep_vec;        /* float4 values per lane                             */
-  uint32_t tile_rows;        /* factor rows per shared-memory tile (0: tile sweeps off) */
-  uint32_t item_tiles;       /* user blocks of the item-pass tile sweep (0: gather kernel) */
-  uint64_t head_nnz;         /* user-pass nonzeros served from the shared-memory head tile */
-  uint64_t tile_segments;    /* segments of both tile sweeps                        */
+  uint32_t user_l2_tiles;    /* L2 tiles of the item rows the user pass is grouped by (1: none) */
+  uint32_t item_l2_tiles;    /* L2 tiles of the user rows the item pass is grouped by (1: none) */
+  uint64_t head_nnz;         /* nonzeros of the most popular items served by the dense
+                                tcgen05 head instead of the gather kernel (0: head off) */
+  uint32_t item_chunks;      /* chunks of the item pass (multi-GPU: one all-reduce each,
+                                overlapped with the sweeps that follow)             */
+  uint32_t mg_exact;         /* 1: the item side's fallback buffers ride in the all-reduce
+                                (set after a fallback fired on a multi-GPU run)     */
   float    last_topn_ms;     /* device time of the scoring + selection kernel(s) of
                                 the last hpf_topn                                   */
+  uint32_t n_devices;        /* GPUs this ctx drives                                */
 } hpf_stats;
 
 /* Fill *cfg with the reference's defaults (all priors 0.3, device 0). */

@@ -168,44 +168,92 @@ def test_two_gpu_shards_match_single_gpu_and_oracle(flags):
     assert not bad, bad
 
 
+def _run_two_ranks(d, s, flags, iters, k, state=None, want_stats=False):
+    """Two engines (GPU 0 and 1, one thread each) joined by NCCL over the nnz-balanced user partition."""
+    n, m = d["n"], d["m"]
+    bounds = H.partition_users(d["row_ptr"], 2)
+    rp = d["row_ptr"].astype(np.int64)
+    uid = H.comm_unique_id()
+    out, errs = [None, None], []
+
+    def worker(r):
+        try:
+            lo, hi = int(bounds[r]), int(bounds[r + 1])
+            with H.Engine(hi - lo, m, k, flags=flags, device=r, n_users_global=n) as e:
+                e.comm_init(r, 2, uid)
+                e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], None if d["y"] is None else d["y"][rp[lo]:rp[hi]])
+                util.push_state(e, s, users=np.arange(lo, hi))
+                e.iterate(iters)
+                out[r] = ({g: e.get_state(util._IDS[g]) for g in util.groups(s)}, e.stats())
+        except Exception as ex:  # surfaced in the main thread
+            errs.append(ex)
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    return out
+
+
+def _stitch(out, s, n, m, k, flags):
+    got = O.OracleState(n, m, k, flags)
+    for g in util.groups(s):
+        for f in O.FIELDS:
+            if g.startswith("beta") or (g == "theta" and f == "rate" and not (flags & H.HIER)):
+                np.testing.assert_array_equal(out[0][0][g][f], out[1][0][g][f])  # replicas stay bitwise identical
+                got.p[g][f][...] = out[0][0][g][f].reshape(got.p[g][f].shape)
+            else:
+                got.p[g][f][...] = np.concatenate([out[0][0][g][f], out[1][0][g][f]]).reshape(got.p[g][f].shape)
+    return got
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [H.HIER | H.BIAS, 0])
-def test_two_gpu_allreduce_overlap_is_bitwise_the_default(monkeypatch, flags):
-    """HPF_AR_OVERLAP=1 (opt-in): [T_beta | Tb_beta] reduced on a second stream under the theta update, the Kp column
-    sums afterwards.  Same operands, two ranks: every sum is a + b either way, so the state must not change by a bit."""
+@pytest.mark.parametrize("flags,dense", [(H.HIER | H.BIAS, "0"), (0, "0"), (H.HIER, "1")])
+def test_two_gpu_chunked_allreduce_is_bitwise_the_single_allreduce(monkeypatch, flags, dense):
+    """The item pass runs in chunks of items and the all-reduce of a finished chunk's T_beta rows runs on the
+    communication stream under the sweeps that follow (HPF_AR_CHUNKS; default from the payload size).  Same operands,
+    two ranks: every sum is a + b whatever the chunking, so the state must not change by a bit -- a missing
+    stream dependency would show up here."""
     if not _two_gpus():
         pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    monkeypatch.setenv("HPF_DENSE_HEAD", dense)
     n, m, nnz, k, iters = 4000, 1000, 150000, 64, 3
     d = synth.make_ratings(n, m, nnz, seed=41, heldout=0.05)
     s = O.OracleState(n, m, k, flags).init(42)
-    bounds = H.partition_users(d["row_ptr"], 2)
-    rp = d["row_ptr"].astype(np.int64)
     runs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("HPF_AR_OVERLAP", mode)  # read by hpf_comm_init
-        uid = H.comm_unique_id()
-        out, errs = [None, None], []
-
-        def worker(r):
-            try:
-                lo, hi = int(bounds[r]), int(bounds[r + 1])
-                with H.Engine(hi - lo, m, k, flags=flags, device=r, n_users_global=n) as e:
-                    e.comm_init(r, 2, uid)
-                    e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], d["y"][rp[lo]:rp[hi]])
-                    util.push_state(e, s, users=np.arange(lo, hi))
-                    e.iterate(iters)
-                    out[r] = {g: e.get_state(util._IDS[g]) for g in util.groups(s)}
-            except Exception as ex:  # surfaced in the main thread
-                errs.append(ex)
-
-        ts = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join(timeout=600)
-        assert not errs, errs
-        runs[mode] = out
+    for chunks in ("1", "5"):
+        monkeypatch.setenv("HPF_AR_CHUNKS", chunks)
+        runs[chunks] = _run_two_ranks(d, s, flags, iters, k)
+        assert runs[chunks][0][1]["item_chunks"] == int(chunks)
+        assert (runs[chunks][0][1]["head_nnz"] > 0) == (dense == "1")
     for r in range(2):
         for g in util.groups(s):
             for f in O.FIELDS:
-                np.testing.assert_array_equal(runs["0"][r][g][f], runs["1"][r][g][f], err_msg="rank %d %s.%s" % (r, g, f))
+                np.testing.assert_array_equal(runs["1"][r][0][g][f], runs["5"][r][0][g][f], err_msg="rank %d %s.%s" % (r, g, f))
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8)
+    assert not util.compare_states(_stitch(runs["5"], s, n, m, k, flags), want, rel=6e-5, elog_abs=6e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [H.HIER, H.BIAS])
+def test_two_gpu_exact_fallback_is_reduced_over_the_ranks(flags):
+    """A nonzero whose product form leaves the fp32 range adds y*phi to rank-local fallback buffers; on the item side
+    those have to be summed over the ranks like T_beta.  The engine runs optimistically (no extra traffic), the ranks
+    agree on a 'fallback fired' flag that rides with the column sums, and hpf_iterate re-runs its window from a
+    snapshot with the buffers inside the all-reduce (stats.mg_exact).  State as in the single-GPU test: user rows
+    peaked in one factor, item rows in another, 200 nats apart -- EVERY nonzero takes the fallback."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 900, 400, 30000, 12, 2
+    d = synth.make_ratings(n, m, nnz, seed=5)
+    s = O.OracleState(n, m, k, flags).init(6)
+    s.p["theta"]["Elogv"][:, 1:] -= 200.0
+    s.p["beta"]["Elogv"][:, :-1] -= 200.0
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters)
+    out = _run_two_ranks(d, s, flags, iters, k)
+    assert out[0][1]["mg_exact"] == 1 and out[1][1]["mg_exact"] == 1
+    assert out[0][1]["slow_path_nnz"] > 0
+    bad = util.compare_states(_stitch(out, s, n, m, k, flags), want, rel=6e-5, elog_abs=6e-5)
+    assert not bad, bad

@@ -13,6 +13,8 @@ import pytest
 import util
 from oracle import hpf_oracle as O
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_digamma_matches_scipy():
     from scipy.special import digamma
@@ -193,3 +195,47 @@ def test_oracle_matches_live_reference_run():
             np.testing.assert_allclose(s.p[gname][f], want.p[gname][f], rtol=1e-12, atol=1e-13)
     # and the reference's own logl() on that state (the harness calls it; printed with "%.5f")
     assert abs(s.elbo(d0["csr.row_ptr"], d0["csr.col_idx"], d0["csr.y"]) - float(d2["elbo"][0])) <= util.TOL_ELBO_REF_PRINT
+
+
+# ------------------------------------------------------------------ C1: the real MovieLens-1M fixture, K=100, 20 iterations
+def test_oracle_and_host_reader_pinned_on_movielens_k100_t20(tmp_path):
+    """BASELINE configs[0]: example/HPF-KDD-movielens.tgz with scripts/run.pl:109-111's flags, -hier, K=100, seed 111.
+    The C++ host reader + start state (hgaprec_hostcheck) on the real files, then the plain-C restatement for 10 and
+    20 iterations (all host cores), against what the UNMODIFIED reference produced (tests/golden/movielens/ref_T20.npz:
+    fp64 row sums, column sums and 4096 sampled entries of every matrix, its held-out sums).  Generation-time figures
+    over the full states: bit-identical single-threaded, 1.6e-8 max rel threaded (oracle_pin.json)."""
+    import json
+    import subprocess
+    host = os.path.join(ROOT, "hgaprec_b200", "host")
+    subprocess.check_call(["make", "-C", host, "../bin/hgaprec_hostcheck"], stdout=subprocess.DEVNULL)
+    pin = json.load(open(os.path.join(util.MOVIELENS, "oracle_pin.json")))
+    assert pin["T20_max_rel_oracle_vs_reference_1thread"] == 0.0 and pin["T20_max_rel_oracle_vs_reference_threaded"] < 1e-6
+    data = util.write_movielens(str(tmp_path / "movielens"))
+    out = str(tmp_path / "dump.bin")
+    subprocess.check_call([os.path.join(ROOT, "hgaprec_b200", "bin", "hgaprec_hostcheck"), "-dir", data, "-out", out] + util.MOVIELENS_FLAGS)
+    d = O.read_dump(out)
+    z = np.load(os.path.join(util.MOVIELENS, "ref_T20.npz"))
+    # the reader on the real files: same seq numbering, same CSR (checksums), same held-out counts as the reference
+    np.testing.assert_array_equal(d["seq2user"], z["seq2user"])
+    np.testing.assert_array_equal(d["seq2movie"], z["seq2movie"])
+    chk = [int(d["csr.row_ptr"].sum()), int(d["csr.col_idx"].astype(np.uint64).sum()), int(d["csr.y"].astype(np.uint64).sum()),
+           len(d["csr.col_idx"]), len(d["validation.u"]), len(d["test.u"])]
+    assert chk == [int(v) for v in z["csr.checksum"]]
+    assert len(d["csr.col_idx"]) == pin["nnz_train"] == 792166
+    s = O.state_from_dump(dict(d, meta=np.array([6040, 3681, 100, 0, 1, 0, 0, 1], dtype=np.float64)))
+    csr = (d["csr.row_ptr"], d["csr.col_idx"], d["csr.y"])
+    for T in (10, 20):
+        s.iterate(*csr, 10, nthreads=os.cpu_count() or 1)
+        fp = util.fingerprint(s)
+        for key, val in fp.items():
+            ref = z["T%d/fp/%s" % (T, key)]
+            if key.endswith("sample_idx"):
+                np.testing.assert_array_equal(val, ref)
+            else:
+                np.testing.assert_allclose(val, ref, rtol=2e-6, atol=1e-12, err_msg="T=%d %s" % (T, key))
+        for split in ("validation", "test"):
+            ll = s.heldout(d[split + ".u"], d[split + ".i"], d[split + ".y"])
+            assert abs(ll - float(z["T%d/%s.ll_sum" % (T, split)][0])) <= 1e-6 * abs(ll), (T, split)
+    # and the reference CLI's own report agrees with its harness dump (validation.txt row of iteration 20)
+    row = open(os.path.join(util.MOVIELENS, "cli", "validation.txt")).read().splitlines()[-1].split("\t")
+    assert int(row[0]) == 20 and int(row[3]) == 8001

@@ -120,3 +120,39 @@ def write_dataset(g, path, extra_lines=(), lift=0):
     with open(os.path.join(path, "test_users.tsv"), "w") as f:
         for u in sorted(set(g["test.u"].tolist())):
             f.write("%d\n" % uid[u])
+
+
+# ---- the real MovieLens-1M fixture (BASELINE configs[0]); tests/golden/make_movielens_golden.py
+MOVIELENS = os.path.join(GOLDEN, "movielens")
+MOVIELENS_FLAGS = ["-n", "6040", "-m", "3681", "-k", "100", "-rating-threshold", "4", "-hier", "-seed", "111"]
+
+
+def write_movielens(path):
+    """train.tsv / validation.tsv / test.tsv / test_users.tsv exactly as the reference's example archive holds them
+    (same lines in the same order), from the compact copy under tests/golden/movielens/data.npz."""
+    os.makedirs(path, exist_ok=True)
+    z = np.load(os.path.join(MOVIELENS, "data.npz"))
+    for split in ("train", "validation", "test"):
+        a = np.stack([z[split + "_u"].astype(np.int64), z[split + "_i"].astype(np.int64), z[split + "_y"].astype(np.int64)], 1)
+        np.savetxt(os.path.join(path, split + ".tsv"), a, fmt="%d", delimiter="\t")
+    np.savetxt(os.path.join(path, "test_users.tsv"), z["test_users"].astype(np.int64), fmt="%d")
+    return path
+
+
+def fingerprint(state, rng_seed=20131103, sample=4096):
+    """Same reduction as make_movielens_golden.fingerprint: fp64 row sums, column sums and fixed sampled entries."""
+    rng = np.random.default_rng(rng_seed)
+    out = {}
+    for g in ("theta", "beta", "thetarate", "betarate"):
+        for f in O.FIELDS:
+            a = state.p[g][f]
+            key = "%s.%s" % (g, f)
+            if a.ndim == 2:
+                out[key + ".rowsum"] = a.sum(axis=1)
+                out[key + ".colsum"] = a.sum(axis=0)
+                idx = rng.integers(0, a.size, sample)
+                out[key + ".sample_idx"] = idx.astype(np.uint32)
+                out[key + ".sample"] = a.reshape(-1)[idx]
+            else:
+                out[key] = a.copy()
+    return out
