@@ -17,7 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HPF_LIB") or os.path.join(HERE, "libhpf_b200.so")  # HPF_LIB: tuning variants
 CSRC = os.path.join(HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_DEVICES = 16
 HIER, BIAS, BINARY, JACOBI, LOGL = 1, 2, 4, 8, 16
 THETA, BETA, THETARATE, BETARATE, THETABIAS, BETABIAS = range(6)
 COMM_ID_BYTES = 128
@@ -38,7 +39,8 @@ class _Config(ctypes.Structure):
                 ("thetarate_shape", ctypes.c_double), ("thetarate_rate", ctypes.c_double),
                 ("betarate_shape", ctypes.c_double), ("betarate_rate", ctypes.c_double),
                 ("thetabias_shape", ctypes.c_double), ("thetabias_rate", ctypes.c_double),
-                ("betabias_shape", ctypes.c_double), ("betabias_rate", ctypes.c_double)]
+                ("betabias_shape", ctypes.c_double), ("betabias_rate", ctypes.c_double),
+                ("n_devices", ctypes.c_uint32), ("devices", ctypes.c_int32 * MAX_DEVICES)]
 
 
 class Stats(ctypes.Structure):
@@ -128,12 +130,17 @@ def comm_unique_id():
 class Engine:
     """One hpf_ctx: the variational state of one user shard on one GPU."""
 
-    def __init__(self, n_users, n_items, k, flags=HIER, device=0, n_users_global=0, **priors):
+    def __init__(self, n_users, n_items, k, flags=HIER, device=0, n_users_global=0, devices=None, **priors):
+        """devices: a list of CUDA ordinals -> ONE ctx that shards its users over those GPUs (hpf_config.n_devices)."""
         self._L = load_library()
         cfg = _Config()
         self._L.hpf_config_default(ctypes.byref(cfg))
         cfg.n_users, cfg.n_items, cfg.k, cfg.flags, cfg.device = int(n_users), int(n_items), int(k), int(flags), int(device)
         cfg.n_users_global = int(n_users_global)
+        if devices is not None:
+            cfg.n_devices = len(devices)
+            for j, dv in enumerate(devices):
+                cfg.devices[j] = int(dv)
         for name, val in priors.items():
             setattr(cfg, name, float(val))
         self.n, self.m, self.k, self.flags = int(n_users), int(n_items), int(k), int(flags)

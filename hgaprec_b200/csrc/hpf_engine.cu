@@ -36,6 +36,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace hpf;
@@ -70,6 +71,7 @@ struct NcclApi {
   void *handle = nullptr;
   int (*GetUniqueId)(ncclUniqueId *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -84,6 +86,7 @@ struct NcclApi {
     if (!handle) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
     GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+    CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
     AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
@@ -223,6 +226,10 @@ struct hpf_ctx {
   // stats
   uint64_t launches = 0, iterations = 0;
   float last_ms = 0.f, last_topn_ms = 0.f;
+  // group ctx (hpf_config.n_devices > 1): owns one child ctx per device and only routes; every field above is unused
+  bool is_group = false;
+  std::vector<hpf_ctx *> kids;
+  std::vector<uint32_t> bounds; // first user of each child's range, then n_users
 };
 
 namespace {
@@ -821,6 +828,17 @@ int ensure_aux(hpf_ctx *c)
 }
 
 // ---- collectives: all on comm_stream, ordered against the compute stream through events ---------------------
+int comm_streams(hpf_ctx *c) // after c->comm / c->nranks are set
+{
+  if (c->nranks > 1 && !c->comm_stream) {
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_theta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
 int nccl_fail(hpf_ctx *c, int rc, const char *what)
 {
   return fail(c, HPF_ENCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
@@ -957,6 +975,20 @@ int stage_in(hpf_ctx *c, const double *host, size_t count, double **dev)
   return 0;
 }
 
+// ---- group ctx (hpf_config.n_devices > 1): defined at the end of this file ----
+int group_create(const hpf_config *cfg, hpf_ctx **out);
+int group_set_ratings(hpf_ctx *g, const uint64_t *row_ptr, const uint32_t *col_idx, const uint8_t *y);
+int group_set_state(hpf_ctx *g, int which, const double *shape, const double *rate, const double *Ev, const double *Elogv);
+int group_get_state(hpf_ctx *g, int which, double *shape, double *rate, double *Ev, double *Elogv);
+int group_iterate(hpf_ctx *g, uint32_t n_iters, hpf_iter_profile *prof);
+int group_heldout(hpf_ctx *g, const uint32_t *u, const uint32_t *i, const uint8_t *y, uint64_t npairs, double *sum_ll);
+int group_elbo(hpf_ctx *g, double *out);
+int group_topn(hpf_ctx *g, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx, uint32_t topn,
+               uint32_t *items_out, float *scores_out);
+int group_item_ranks(hpf_ctx *g, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx,
+                     const uint64_t *query_ptr, const uint32_t *query_idx, uint32_t *rank_out, float *score_out);
+int group_get_stats(const hpf_ctx *g, hpf_stats *out);
+
 } // namespace
 
 // =============================================================================
@@ -984,13 +1016,16 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (cfg->k == 0 || cfg->k > 1024) return fail(c, HPF_EINVAL, "k=%u out of range [1,1024]", cfg->k);
   if (cfg->n_items == 0) return fail(c, HPF_EINVAL, "n_items must be > 0");
   if (cfg->n_users == 0) return fail(c, HPF_EINVAL, "n_users must be > 0 (an empty user shard: use fewer ranks)");
+  if (cfg->n_devices > 1) return group_create(cfg, out);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(c, HPF_ENODEVICE, "no CUDA device available (libhpf_b200 has no CPU path)");
-  if (cfg->device < 0 || cfg->device >= ndev) return fail(c, HPF_EINVAL, "device %d not in [0,%d)", cfg->device, ndev);
-  CU(cudaSetDevice(cfg->device));
+  const int device = cfg->n_devices == 1 ? cfg->devices[0] : cfg->device;
+  if (device < 0 || device >= ndev) return fail(c, HPF_EINVAL, "device %d not in [0,%d)", device, ndev);
+  CU(cudaSetDevice(device));
   hpf_ctx *n = new hpf_ctx();
   n->cfg = *cfg;
+  n->cfg.device = device;
   n->K = cfg->k; n->Kp = (cfg->k + 3u) & ~3u; n->K4 = n->Kp / 4;
   if (n->Kp >= 32) n->ld = (n->Kp + 31u) & ~31u;
   else for (n->ld = 4; n->ld < n->Kp; n->ld *= 2) {}
@@ -1064,6 +1099,11 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
 void hpf_destroy(hpf_ctx *c)
 {
   if (!c) return;
+  if (c->is_group) {
+    for (hpf_ctx *k : c->kids) hpf_destroy(k);
+    delete c;
+    return;
+  }
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
@@ -1085,6 +1125,7 @@ void hpf_destroy(hpf_ctx *c)
 int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col_idx, const uint8_t *y)
 {
   if (!c || !row_ptr) return fail(c, HPF_EINVAL, "null argument");
+  if (c->is_group) return group_set_ratings(c, row_ptr, col_idx, y);
   CU(cudaSetDevice(c->cfg.device));
   const uint32_t n = c->cfg.n_users, m = c->cfg.n_items;
   const uint64_t nnz = row_ptr[n];
@@ -1297,6 +1338,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
 int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate, const double *Ev, const double *Elogv)
 {
   if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  if (c->is_group) return group_set_state(c, which, shape, rate, Ev, Elogv);
   CU(cudaSetDevice(c->cfg.device));
   const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
   Side &s = theta_side ? c->th : c->be;
@@ -1371,6 +1413,7 @@ int hpf_set_state(hpf_ctx *c, int which, const double *shape, const double *rate
 int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev, double *Elogv)
 {
   if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  if (c->is_group) return group_get_state(c, which, shape, rate, Ev, Elogv);
   CU(cudaSetDevice(c->cfg.device));
   const bool theta_side = which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS;
   Side &s = theta_side ? c->th : c->be;
@@ -1492,6 +1535,7 @@ extern "C" {
 int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
 {
   if (!c) return fail(c, HPF_EINVAL, "null ctx");
+  if (c->is_group) return group_iterate(c, n_iters, nullptr);
   CU(cudaSetDevice(c->cfg.device));
   TRY(check_ready(c));
   TRY(ensure_aux(c));
@@ -1529,6 +1573,7 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
   if (!c || !out) return fail(c, HPF_EINVAL, "null argument");
   memset(out, 0, sizeof *out);
   if (n_iters == 0) return 0;
+  if (c->is_group) return group_iterate(c, n_iters, out);
   CU(cudaSetDevice(c->cfg.device));
   TRY(check_ready(c));
   TRY(ensure_aux(c));
@@ -1561,6 +1606,7 @@ int hpf_heldout_loglik(hpf_ctx *c, const uint32_t *u, const uint32_t *i, const u
   *sum_ll = 0.0;
   if (npairs == 0) return 0;
   if (!u || !i || !y) return fail(c, HPF_EINVAL, "null pair arrays");
+  if (c->is_group) return group_heldout(c, u, i, y, npairs, sum_ll);
   CU(cudaSetDevice(c->cfg.device));
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   for (uint64_t p = 0; p < npairs; ++p)
@@ -1599,6 +1645,7 @@ int hpf_elbo(hpf_ctx *c, double *elbo_out)
 {
   if (!c || !elbo_out) return fail(c, HPF_EINVAL, "null argument");
   *elbo_out = 0.0;
+  if (c->is_group) return group_elbo(c, elbo_out);
   if (!c->logl) return fail(c, HPF_EINVAL, "hpf_elbo needs a ctx created with HPF_LOGL");
   TRY(check_ready(c));
   if (c->hier && !c->pr_prev_valid)
@@ -1674,6 +1721,7 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
   if (!c) return fail(c, HPF_EINVAL, "null ctx");
   if (nu == 0) return 0;
   if (!users || !items_out || !scores_out) return fail(c, HPF_EINVAL, "null argument");
+  if (c->is_group) return group_topn(c, users, nu, excl_ptr, excl_idx, topn, items_out, scores_out);
   if (topn == 0 || topn > (uint32_t)topk::kMaxTopN) return fail(c, HPF_EINVAL, "topn=%u out of range [1,%d]", topn, topk::kMaxTopN);
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
@@ -1783,6 +1831,7 @@ int hpf_item_ranks(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_
   if (!c) return fail(c, HPF_EINVAL, "null ctx");
   if (nu == 0) return 0;
   if (!users || !query_ptr || !rank_out || !score_out) return fail(c, HPF_EINVAL, "null argument");
+  if (c->is_group) return group_item_ranks(c, users, nu, excl_ptr, excl_idx, query_ptr, query_idx, rank_out, score_out);
   if (!c->th.have_state || !c->be.have_state) return fail(c, HPF_EINVAL, "state has not been set");
   if (c->bias && (!c->th.have_bias || !c->be.have_bias)) return fail(c, HPF_EINVAL, "bias state has not been set");
   CU(cudaSetDevice(c->cfg.device));
@@ -1882,6 +1931,7 @@ int hpf_comm_init(hpf_ctx *c, int rank, int nranks, const void *id, size_t id_by
 {
   if (!c || !id || id_bytes < sizeof(ncclUniqueId) || nranks < 1 || rank < 0 || rank >= nranks)
     return fail(c, HPF_EINVAL, "bad communicator arguments");
+  if (c->is_group) return fail(c, HPF_EINVAL, "a ctx with n_devices > 1 owns its communicator (one box); hpf_comm_init is for one-device ctxs");
   CU(cudaSetDevice(c->cfg.device));
   std::string err;
   if (!g_nccl.load(err)) return fail(c, HPF_ENCCL, "%s", err.c_str());
@@ -1890,20 +1940,15 @@ int hpf_comm_init(hpf_ctx *c, int rank, int nranks, const void *id, size_t id_by
   int rc = g_nccl.CommInitRank(&c->comm, nranks, uid, rank);
   if (rc != ncclSuccess) return fail(c, HPF_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
   c->rank = rank; c->nranks = nranks;
-  if (nranks > 1 && !c->comm_stream) {
-    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-    for (auto &e : c->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_theta, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
-  }
   // ratings planned before the communicator existed have one chunk: still correct, the all-reduce just overlaps less
-  return 0;
+  return comm_streams(c);
 }
 
 int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
 {
   if (!c || !out) return HPF_EINVAL;
   memset(out, 0, sizeof *out);
+  if (c->is_group) return group_get_stats(c, out);
   out->kernel_launches = c->launches;
   out->iterations = c->iterations;
   unsigned long long sc = 0;
@@ -1926,3 +1971,305 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
 }
 
 } // extern "C"
+
+// =============================================================================
+// group ctx: ONE ctx, several GPUs of one box (hpf_config.n_devices > 1).  The reference is one process
+// (SURVEY.md 8b "threading"); this is the form its command line uses (`hgaprec -gpus N`).  The group owns one
+// ordinary one-device ctx per GPU ("kid"), shards the users over them with hpf_partition_users at the first
+// hpf_set_ratings_csr, joins them with ncclCommInitAll and drives each kid from its own worker thread inside a call
+// -- exactly the configuration the 2-GPU tests exercise with explicit threads.  Every argument and result of the ABI
+// keeps GLOBAL user numbers.
+// =============================================================================
+namespace {
+
+template <class F> int for_each_kid(hpf_ctx *g, F f)
+{
+  const size_t nk = g->kids.size();
+  std::vector<int> rc(nk, 0);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < nk; ++i) th.emplace_back([&, i]() { rc[i] = f(i, g->kids[i]); });
+  for (auto &t : th) t.join();
+  for (size_t i = 0; i < nk; ++i)
+    if (rc[i] != 0) {
+      g->err = "device " + std::to_string(g->kids[i]->cfg.device) + ": " + g->kids[i]->err;
+      return rc[i];
+    }
+  return 0;
+}
+
+// one ordinary ctx per device over the user ranges b[0..nd], joined by ncclCommInitAll
+int group_make_kids(hpf_ctx *g, const std::vector<uint32_t> &b)
+{
+  const uint32_t nd = g->cfg.n_devices;
+  for (uint32_t i = 0; i < nd; ++i)
+    if (b[i + 1] <= b[i]) return fail(g, HPF_EINVAL, "the user partition leaves device %u without users; use fewer devices", i);
+  std::vector<ncclComm_t> comms(nd);
+  std::vector<int> devs(g->cfg.devices, g->cfg.devices + nd);
+  const int rc = g_nccl.CommInitAll(comms.data(), (int)nd, devs.data());
+  if (rc != ncclSuccess) return fail(g, HPF_ENCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  for (uint32_t i = 0; i < nd; ++i) {
+    hpf_config kc = g->cfg;
+    kc.n_devices = 0; kc.device = devs[i];
+    kc.n_users = b[i + 1] - b[i];
+    kc.n_users_global = g->cfg.n_users_global ? g->cfg.n_users_global : g->cfg.n_users;
+    hpf_ctx *k = nullptr;
+    const int krc = hpf_create(&kc, &k);
+    if (krc != 0) {
+      g->err = "device " + std::to_string(devs[i]) + ": " + g_create_error;
+      for (hpf_ctx *q : g->kids) hpf_destroy(q);
+      g->kids.clear();
+      for (uint32_t j = i; j < nd; ++j) g_nccl.CommDestroy(comms[j]);
+      return krc;
+    }
+    k->comm = comms[i]; k->rank = (int)i; k->nranks = (int)nd;
+    g->kids.push_back(k);
+  }
+  g->bounds = b;
+  for (hpf_ctx *k : g->kids) {
+    cudaSetDevice(k->cfg.device);
+    TRY(comm_streams(k));
+  }
+  return 0;
+}
+
+// calls that can come before any ratings (hpf_set_state ahead of hpf_topn in `-gen-ranking`): equal user counts
+int group_need_kids(hpf_ctx *g)
+{
+  if (!g->kids.empty()) return 0;
+  const uint32_t nd = g->cfg.n_devices;
+  std::vector<uint32_t> b(nd + 1);
+  for (uint32_t i = 0; i <= nd; ++i) b[i] = (uint32_t)(((uint64_t)g->cfg.n_users * i) / nd);
+  return group_make_kids(g, b);
+}
+
+uint32_t owner_of(const hpf_ctx *g, uint32_t user)
+{
+  return (uint32_t)(std::upper_bound(g->bounds.begin(), g->bounds.end(), user) - g->bounds.begin()) - 1u;
+}
+
+int group_create(const hpf_config *cfg, hpf_ctx **out)
+{
+  hpf_ctx *c = nullptr;
+  if (cfg->n_devices > HPF_MAX_DEVICES) return fail(c, HPF_EINVAL, "n_devices=%u > %d", cfg->n_devices, HPF_MAX_DEVICES);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(c, HPF_ENODEVICE, "no CUDA device available (libhpf_b200 has no CPU path)");
+  for (uint32_t i = 0; i < cfg->n_devices; ++i) {
+    if (cfg->devices[i] < 0 || cfg->devices[i] >= ndev) return fail(c, HPF_EINVAL, "devices[%u]=%d not in [0,%d)", i, cfg->devices[i], ndev);
+    for (uint32_t j = 0; j < i; ++j)
+      if (cfg->devices[j] == cfg->devices[i]) return fail(c, HPF_EINVAL, "device %d listed twice", cfg->devices[i]);
+  }
+  if (cfg->n_users < cfg->n_devices) return fail(c, HPF_EINVAL, "fewer users (%u) than devices (%u)", cfg->n_users, cfg->n_devices);
+  std::string err;
+  if (!g_nccl.load(err)) return fail(c, HPF_ENCCL, "%s", err.c_str());
+  if (!g_nccl.CommInitAll) return fail(c, HPF_ENCCL, "libnccl lacks ncclCommInitAll");
+  hpf_ctx *g = new hpf_ctx();
+  g->cfg = *cfg;
+  g->is_group = true;
+  g->K = cfg->k;
+  g->hier = cfg->flags & HPF_HIER; g->bias = cfg->flags & HPF_BIAS;
+  *out = g;
+  return 0;
+}
+
+int group_set_ratings(hpf_ctx *g, const uint64_t *row_ptr, const uint32_t *col_idx, const uint8_t *y)
+{
+  const uint32_t n = g->cfg.n_users, nd = g->cfg.n_devices;
+  if (g->kids.empty()) { // the first ratings fix the partition: contiguous user ranges balanced by nonzeros
+    std::vector<uint32_t> b(nd + 1);
+    TRY(hpf_partition_users(row_ptr, n, nd, b.data()));
+    TRY(group_make_kids(g, b));
+  }
+  // every kid gets its slice of the CSR (row pointer rebased), all uploads and device set-up side by side
+  return for_each_kid(g, [&](size_t i, hpf_ctx *k) {
+    const uint32_t lo = g->bounds[i], hi = g->bounds[i + 1];
+    std::vector<uint64_t> rp((size_t)hi - lo + 1);
+    for (uint32_t u = lo; u <= hi; ++u) rp[u - lo] = row_ptr[u] - row_ptr[lo];
+    return hpf_set_ratings_csr(k, rp.data(), col_idx ? col_idx + row_ptr[lo] : nullptr, y ? y + row_ptr[lo] : nullptr);
+  });
+}
+
+bool user_side(int which) { return which == HPF_THETA || which == HPF_THETARATE || which == HPF_THETABIAS; }
+
+int group_set_state(hpf_ctx *g, int which, const double *shape, const double *rate, const double *Ev, const double *Elogv)
+{
+  TRY(group_need_kids(g));
+  const size_t K = g->K;
+  return for_each_kid(g, [&](size_t i, hpf_ctx *k) {
+    if (!user_side(which)) return hpf_set_state(k, which, shape, rate, Ev, Elogv); // replicated
+    const size_t lo = g->bounds[i];
+    const size_t w = which == HPF_THETA ? K : 1;                                    // doubles per row
+    const size_t wr = which == HPF_THETA && !g->hier ? 0 : w;                        // GR rate: one K-vector for all rows
+    auto at = [&](const double *p, size_t width) { return p ? p + lo * width : nullptr; };
+    return hpf_set_state(k, which, at(shape, w), at(rate, wr), at(Ev, w), at(Elogv, w));
+  });
+}
+
+int group_get_state(hpf_ctx *g, int which, double *shape, double *rate, double *Ev, double *Elogv)
+{
+  TRY(group_need_kids(g));
+  if (!user_side(which)) { // replicated, bitwise identical on every device
+    const int rc = hpf_get_state(g->kids[0], which, shape, rate, Ev, Elogv);
+    if (rc) g->err = g->kids[0]->err;
+    return rc;
+  }
+  const size_t K = g->K;
+  return for_each_kid(g, [&](size_t i, hpf_ctx *k) {
+    const size_t lo = g->bounds[i];
+    const size_t w = which == HPF_THETA ? K : 1;
+    const size_t wr = which == HPF_THETA && !g->hier ? 0 : w;
+    auto at = [&](double *p, size_t width) { return p ? p + lo * width : nullptr; };
+    // the GR rate vector is the same on every kid: only kid 0 writes it
+    return hpf_get_state(k, which, at(shape, w), (wr == 0 && i != 0) ? nullptr : at(rate, wr), at(Ev, w), at(Elogv, w));
+  });
+}
+
+int group_iterate(hpf_ctx *g, uint32_t n_iters, hpf_iter_profile *prof)
+{
+  TRY(group_need_kids(g));
+  std::vector<hpf_iter_profile> pr(g->kids.size());
+  TRY(for_each_kid(g, [&](size_t i, hpf_ctx *k) { return prof ? hpf_iterate_profiled(k, n_iters, &pr[i]) : hpf_iterate(k, n_iters); }));
+  g->last_ms = 0.f;
+  for (hpf_ctx *k : g->kids) g->last_ms = std::max(g->last_ms, k->last_ms);
+  if (prof) { // per stage: the slowest device
+    *prof = pr[0];
+    for (auto &p : pr) {
+      float *a = reinterpret_cast<float *>(prof);
+      const float *b = reinterpret_cast<const float *>(&p);
+      for (size_t q = 0; q < sizeof(hpf_iter_profile) / sizeof(float); ++q) a[q] = std::max(a[q], b[q]);
+    }
+  }
+  return 0;
+}
+
+int group_heldout(hpf_ctx *g, const uint32_t *u, const uint32_t *i, const uint8_t *y, uint64_t npairs, double *sum_ll)
+{
+  TRY(group_need_kids(g));
+  const size_t nk = g->kids.size();
+  std::vector<std::vector<uint32_t>> ku(nk), ki(nk);
+  std::vector<std::vector<uint8_t>> ky(nk);
+  for (uint64_t p = 0; p < npairs; ++p) {
+    if (u[p] >= g->cfg.n_users) return fail(g, HPF_EINVAL, "pair %llu out of range", (unsigned long long)p);
+    const uint32_t o = owner_of(g, u[p]);
+    ku[o].push_back(u[p] - g->bounds[o]); ki[o].push_back(i[p]); ky[o].push_back(y[p]);
+  }
+  std::vector<double> part(nk, 0.0);
+  TRY(for_each_kid(g, [&](size_t q, hpf_ctx *k) { return hpf_heldout_loglik(k, ku[q].data(), ki[q].data(), ky[q].data(), ku[q].size(), &part[q]); }));
+  double s = 0.0;
+  for (double v : part) s += v; // device order: repeatable
+  *sum_ll = s;
+  return 0;
+}
+
+int group_elbo(hpf_ctx *g, double *out)
+{
+  TRY(group_need_kids(g));
+  std::vector<double> part(g->kids.size(), 0.0);
+  TRY(for_each_kid(g, [&](size_t q, hpf_ctx *k) { return hpf_elbo(k, &part[q]); }));
+  double s = 0.0;
+  for (double v : part) s += v; // a kid returns its users' part (+ the item-side terms on rank 0): they add up
+  *out = s;
+  return 0;
+}
+
+// users of a query routed to their owners: per kid the positions in the caller's arrays, local user numbers and the
+// rebased pointer array(s)
+struct Routed {
+  std::vector<uint32_t> pos, users;
+  std::vector<uint64_t> eptr, qptr;
+  std::vector<uint32_t> eidx, qidx;
+};
+int route_users(hpf_ctx *g, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx,
+                const uint64_t *query_ptr, const uint32_t *query_idx, std::vector<Routed> *out)
+{
+  out->assign(g->kids.size(), Routed());
+  for (auto &r : *out) { r.eptr.push_back(0); r.qptr.push_back(0); }
+  for (uint32_t a = 0; a < nu; ++a) {
+    if (users[a] >= g->cfg.n_users) return fail(g, HPF_EINVAL, "users[%u]=%u >= n_users=%u", a, users[a], g->cfg.n_users);
+    Routed &r = (*out)[owner_of(g, users[a])];
+    r.pos.push_back(a);
+    r.users.push_back(users[a] - g->bounds[owner_of(g, users[a])]);
+    if (excl_ptr) {
+      if (excl_ptr[a + 1] < excl_ptr[a]) return fail(g, HPF_EINVAL, "excl_ptr not monotone at %u", a);
+      r.eidx.insert(r.eidx.end(), excl_idx + excl_ptr[a], excl_idx + excl_ptr[a + 1]);
+    }
+    r.eptr.push_back(r.eidx.size());
+    if (query_ptr) {
+      if (query_ptr[a + 1] < query_ptr[a]) return fail(g, HPF_EINVAL, "query_ptr not monotone at %u", a);
+      r.qidx.insert(r.qidx.end(), query_idx + query_ptr[a], query_idx + query_ptr[a + 1]);
+      r.qptr.push_back(r.qidx.size());
+    }
+  }
+  return 0;
+}
+
+int group_topn(hpf_ctx *g, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx, uint32_t topn,
+               uint32_t *items_out, float *scores_out)
+{
+  TRY(group_need_kids(g));
+  if (excl_ptr && excl_ptr[nu] > 0 && !excl_idx) return fail(g, HPF_EINVAL, "excl_idx is null");
+  std::vector<Routed> rt;
+  TRY(route_users(g, users, nu, excl_ptr, excl_idx, nullptr, nullptr, &rt));
+  TRY(for_each_kid(g, [&](size_t q, hpf_ctx *k) {
+    Routed &r = rt[q];
+    if (r.users.empty()) return 0;
+    std::vector<uint32_t> items(r.users.size() * (size_t)topn);
+    std::vector<float> scores(r.users.size() * (size_t)topn);
+    const int rc = hpf_topn(k, r.users.data(), (uint32_t)r.users.size(), r.eptr.data(), r.eidx.data(), topn, items.data(), scores.data());
+    if (rc) return rc;
+    for (size_t a = 0; a < r.users.size(); ++a) {
+      memcpy(items_out + (size_t)r.pos[a] * topn, items.data() + a * topn, sizeof(uint32_t) * topn);
+      memcpy(scores_out + (size_t)r.pos[a] * topn, scores.data() + a * topn, sizeof(float) * topn);
+    }
+    return 0;
+  }));
+  g->last_topn_ms = 0.f;
+  for (hpf_ctx *k : g->kids) g->last_topn_ms = std::max(g->last_topn_ms, k->last_topn_ms);
+  return 0;
+}
+
+int group_item_ranks(hpf_ctx *g, const uint32_t *users, uint32_t nu, const uint64_t *excl_ptr, const uint32_t *excl_idx,
+                     const uint64_t *query_ptr, const uint32_t *query_idx, uint32_t *rank_out, float *score_out)
+{
+  TRY(group_need_kids(g));
+  if (query_ptr[nu] > 0 && !query_idx) return fail(g, HPF_EINVAL, "null index array");
+  if (excl_ptr && excl_ptr[nu] > 0 && !excl_idx) return fail(g, HPF_EINVAL, "null index array");
+  std::vector<Routed> rt;
+  TRY(route_users(g, users, nu, excl_ptr, excl_idx, query_ptr, query_idx, &rt));
+  return for_each_kid(g, [&](size_t q, hpf_ctx *k) {
+    Routed &r = rt[q];
+    if (r.users.empty() || r.qidx.empty()) return 0;
+    std::vector<uint32_t> rank(r.qidx.size());
+    std::vector<float> score(r.qidx.size());
+    const int rc = hpf_item_ranks(k, r.users.data(), (uint32_t)r.users.size(), r.eptr.data(), r.eidx.data(), r.qptr.data(), r.qidx.data(),
+                                  rank.data(), score.data());
+    if (rc) return rc;
+    for (size_t a = 0; a < r.users.size(); ++a) { // the caller's queries of user pos[a] start at query_ptr[pos[a]]
+      const uint64_t dst = query_ptr[r.pos[a]], src = r.qptr[a], cnt = r.qptr[a + 1] - r.qptr[a];
+      memcpy(rank_out + dst, rank.data() + src, sizeof(uint32_t) * cnt);
+      memcpy(score_out + dst, score.data() + src, sizeof(float) * cnt);
+    }
+    return 0;
+  });
+}
+
+int group_get_stats(const hpf_ctx *g, hpf_stats *out)
+{
+  out->n_devices = g->cfg.n_devices;
+  out->last_iterate_ms = g->last_ms;
+  out->last_topn_ms = g->last_topn_ms;
+  for (size_t i = 0; i < g->kids.size(); ++i) {
+    hpf_stats s;
+    hpf_get_stats(g->kids[i], &s);
+    out->kernel_launches += s.kernel_launches; out->slow_path_nnz += s.slow_path_nnz; out->nnz += s.nnz;
+    out->device_bytes += s.device_bytes; out->head_nnz += s.head_nnz;
+    if (i == 0) {
+      out->iterations = s.iterations; out->sweep_group = s.sweep_group; out->sweep_vec = s.sweep_vec;
+      out->user_l2_tiles = s.user_l2_tiles; out->item_l2_tiles = s.item_l2_tiles; out->item_chunks = s.item_chunks;
+    }
+    out->mg_exact |= s.mg_exact;
+  }
+  return 0;
+}
+
+} // namespace

@@ -92,6 +92,11 @@ HGAPRec::HGAPRec(Options &opt, Ratings &ratings)
   cfg.flags = (opt_.hier ? HPF_HIER : 0u) | (opt_.bias ? HPF_BIAS : 0u) | (opt_.binary_data ? HPF_BINARY : 0u) |
               (!opt_.vb ? HPF_JACOBI : 0u) | (opt_.logl ? HPF_LOGL : 0u);
   cfg.device = opt_.device;
+  if (opt_.gpus > 1) {
+    if (opt_.gpus > HPF_MAX_DEVICES) opt_.gpus = HPF_MAX_DEVICES;
+    cfg.n_devices = (uint32_t)opt_.gpus;
+    for (int g = 0; g < opt_.gpus; ++g) cfg.devices[g] = g;
+  }
   if (hpf_create(&cfg, &ctx_) != 0) die("hpf_create");
 }
 

@@ -30,11 +30,12 @@ struct Options {
   bool binary_data, bias, hier, vb, logl, gen_ranking;
   bool csr_cache; // -csr-cache (not in the reference): keep / reuse <dir>/train.tsv.hpfcsr, see ratings.hh
   int device;
+  int gpus; // > 1: shard the users over GPUs 0 .. gpus-1 (one ctx, hpf_config.n_devices)
   std::string prefix;   // output directory, Env's naming (src/env.hh:283-369)
   volatile sig_atomic_t *save_state_now;
   Options()
       : n(0), m(0), k(0), rfreq(10), max_iterations(1000), rating_threshold(1), seed(0), a(0.3), b(0.3), c(0.3), d(0.3),
-        binary_data(false), bias(false), hier(false), vb(true), logl(false), gen_ranking(false), csr_cache(false), device(0), save_state_now(0) {}
+        binary_data(false), bias(false), hier(false), vb(true), logl(false), gen_ranking(false), csr_cache(false), device(0), gpus(1), save_state_now(0) {}
   std::string make_prefix() const;
 };
 

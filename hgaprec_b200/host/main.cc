@@ -7,8 +7,9 @@
 // Flags the reference parses but never reads on this path (-a -b -c -d -load
 // -online ...) are accepted with the same arity and ignored the same way; its
 // other-model baselines (-nmf -lda -chi ...: external programs, SURVEY.md 2 rows
-// 12-18) are outside this path and rejected.  One extension: -device G picks the
-// CUDA device.
+// 12-18) are outside this path and rejected.  Extensions: -device G picks the
+// CUDA device, -gpus N shards the users over GPUs 0..N-1 of this box (one process,
+// hpf_config.n_devices), -csr-cache keeps the parsed training matrix beside train.tsv.
 #include <assert.h>
 #include <signal.h>
 #include <stdio.h>
@@ -61,6 +62,7 @@ int main(int argc, char **argv)
     else if (!strcmp(a, "-gen-ranking")) o.gen_ranking = true;
     else if (!strcmp(a, "-rating-threshold")) o.rating_threshold = atoi(NEXT);
     else if (!strcmp(a, "-device")) o.device = atoi(NEXT);
+    else if (!strcmp(a, "-gpus")) o.gpus = atoi(NEXT);
     else if (!strcmp(a, "-csr-cache")) o.csr_cache = true;
     else if (!strcmp(a, "-load") || !strcmp(a, "-nmi") || !strcmp(a, "-wals_l") || !strcmp(a, "-wals_C")) (void)NEXT; // parsed, unused
     else if (!strcmp(a, "-batch") || !strcmp(a, "-p") || !strcmp(a, "-strid") || !strcmp(a, "-gen-heldout") ||

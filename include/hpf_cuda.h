@@ -21,6 +21,11 @@
  *     wrapper maps nonzero to its own lerr()+exit(-1).
  *   - one host thread per ctx; a ctx is not thread-safe.
  *   - there is NO CPU fallback: without a CUDA device hpf_create fails.
+ *   - multi-GPU comes in two forms with identical numerics: (a) hpf_config.n_devices > 1 -- ONE ctx in one
+ *     process drives that many GPUs of the box: the library shards the users (hpf_partition_users), keeps one
+ *     stream, one NCCL rank and one worker thread per device, and every call below takes GLOBAL user numbers
+ *     (this is what the `hgaprec -gpus N` command line uses); (b) one ctx per GPU in separate processes or
+ *     threads joined with hpf_comm_init (what bench.py uses under torchrun), where the caller shards.
  */
 #ifndef HPF_CUDA_H
 #define HPF_CUDA_H
@@ -32,7 +37,8 @@
 extern "C" {
 #endif
 
-#define HPF_ABI_VERSION 1
+#define HPF_ABI_VERSION 2
+#define HPF_MAX_DEVICES 16
 
 #if defined(__GNUC__)
 #define HPF_API __attribute__((visibility("default")))
@@ -75,7 +81,8 @@ typedef struct hpf_ctx hpf_ctx;
 
 typedef struct hpf_config {
   uint32_t abi_version;   /* HPF_ABI_VERSION */
-  uint32_t n_users;       /* users held by THIS ctx (the local shard)              */
+  uint32_t n_users;       /* users held by THIS ctx (the local shard; all users when
+                             n_devices > 1)                                        */
   uint32_t n_items;       /* m: all items (the beta side is replicated per rank)   */
   uint32_t k;             /* factors                                               */
   uint32_t flags;         /* HPF_HIER | HPF_BIAS | HPF_BINARY | HPF_JACOBI          */
@@ -90,6 +97,12 @@ typedef struct hpf_config {
   double betarate_shape, betarate_rate;   /* _betarate (eta)                     */
   double thetabias_shape, thetabias_rate; /* _thetabias                          */
   double betabias_shape, betabias_rate;   /* _betabias                           */
+  /* n_devices > 1: this ctx shards its users over devices[0 .. n_devices) of this box and sums the item
+   * side over NCCL; `device` is ignored.  The user ranges are contiguous and fixed by the first call that
+   * needs them: balanced by nonzeros when that is hpf_set_ratings_csr (training), by user count when the
+   * state is uploaded without ratings (-gen-ranking).  0: one GPU, `device`; 1: one GPU, devices[0].   */
+  uint32_t n_devices;
+  int32_t  devices[HPF_MAX_DEVICES];
 } hpf_config;
 
 /* counters readable after any call (all monotone since hpf_create) */

@@ -12,12 +12,14 @@ and keeps
                       ordinals, src/ratings.hh:117-151, so the order is part of the input); tests write them back
                       out as TSVs -- the GPU box has no /root/reference
   cli/                validation.txt, test.txt, precision.txt, max.txt, param.txt as the reference CLI wrote them
-  ref_T20.npz         E[theta], E[beta] after 20 iterations from oracle/_ref/ref_harness (fp32 copies: the 1e-4
-                      relative-Frobenius gate is three orders above fp32 rounding),
-                      the reference's own held-out sums, plus an fp64 FINGERPRINT of the full T=10 / T=20 states
+  ref_T21.npz         E[theta], E[beta] after 21 iterations from oracle/_ref/ref_harness -- the state the CLI saves in its
+                      report window of iteration 20: vb_hier numbers its iterations from 0 and reports AFTER the update
+                      (src/hgaprec.cc:1337-1425), so "iteration 10 / 20" in validation.txt is the state after 11 / 21
+                      sweeps -- as fp32 copies (the 1e-4 relative-Frobenius gate is three orders above fp32 rounding),
+                      the reference's own held-out sums, plus an fp64 FINGERPRINT of the full T=11 / T=21 states
                       (row sums, column sums and 4096 sampled entries of every matrix) that pins oracle/hpf_oracle.c
                       at K=100 over 20 iterations without committing 30 MB of doubles
-  oracle_pin.json     max relative difference oracle-vs-reference over the FULL fp64 states at T=10 / T=20, measured
+  oracle_pin.json     max relative difference oracle-vs-reference over the FULL fp64 states at T=11 / T=21, measured
                       here at generation time (the CPU test re-checks it through the fingerprint anywhere, and in
                       full where /root/reference exists)
 
@@ -94,7 +96,7 @@ def main():
         os.makedirs(run)
         h0 = subprocess.Popen([O.REF_HARNESS] + base + ["-iters", "0", "-dump", os.path.join(run, "d"), "-label", "h0"],
                               cwd=run, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        h1 = subprocess.Popen([O.REF_HARNESS] + base + ["-iters", "10,20", "-dump", os.path.join(run, "d"), "-label", "h1"],
+        h1 = subprocess.Popen([O.REF_HARNESS] + base + ["-iters", "11,21", "-dump", os.path.join(run, "d"), "-label", "h1"],
                               cwd=run, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         assert h0.wait() == 0
         d0 = O.read_dump(os.path.join(run, "d_0.bin"))
@@ -102,11 +104,11 @@ def main():
         csr = (d0["csr.row_ptr"], d0["csr.col_idx"], d0["csr.y"])
         # ---- the plain-C restatement from the reference's own T=0 state, all cores (rows are independent)
         nt = os.cpu_count() or 1
-        s10 = s.copy().iterate(*csr, 10, nthreads=nt)
+        s10 = s.copy().iterate(*csr, 11, nthreads=nt)
         s20 = s10.copy().iterate(*csr, 10, nthreads=nt)
         assert h1.wait() == 0 and cli.wait() == 0
         # ... and single-threaded (the reference's own summation order)
-        q10 = s.copy().iterate(*csr, 10, nthreads=1)
+        q10 = s.copy().iterate(*csr, 11, nthreads=1)
         q20 = q10.copy().iterate(*csr, 10, nthreads=1)
         pin, out = {"threads": nt}, {}
 
@@ -117,7 +119,7 @@ def main():
                     a, b = mine.p[g][f], ref.p[g][f]
                     w = max(w, float((np.abs(a - b) / np.maximum(np.abs(b), 1e-300)).max()))
             return w
-        for T, mine, single in ((10, s10, q10), (20, s20, q20)):
+        for T, mine, single in ((11, s10, q10), (21, s20, q20)):
             d = O.read_dump(os.path.join(run, "d_%d.bin" % T))
             ref = O.state_from_dump(d)
             pin["T%d_max_rel_oracle_vs_reference_threaded" % T] = worst_rel(mine, ref)
@@ -126,7 +128,7 @@ def main():
                 out["T%d/fp/%s" % (T, kk)] = v
             for split in ("validation", "test"):
                 out["T%d/%s.ll_sum" % (T, split)] = d[split + ".ll_sum"]
-            if T == 20:
+            if T == 21:
                 out["T%d/theta.Ev" % T] = ref.p["theta"]["Ev"].astype(np.float32)
                 out["T%d/beta.Ev" % T] = ref.p["beta"]["Ev"].astype(np.float32)
         for kk in ("seq2user", "seq2movie"):   # the CSR itself is re-derived from data.npz by the host reader under test
@@ -134,7 +136,7 @@ def main():
         out["csr.checksum"] = np.array([int(d0["csr.row_ptr"].sum()), int(d0["csr.col_idx"].astype(np.uint64).sum()),
                                         int(d0["csr.y"].astype(np.uint64).sum()), len(d0["csr.col_idx"]),
                                         len(d0["validation.u"]), len(d0["test.u"])], dtype=np.uint64)
-        np.savez_compressed(os.path.join(DST, "ref_T20.npz"), **out)
+        np.savez_compressed(os.path.join(DST, "ref_T21.npz"), **out)
         fit = [x for x in os.listdir(tmp) if x.startswith("n%d-" % N)]
         assert len(fit) == 1, fit
         for f in KEEP:

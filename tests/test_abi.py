@@ -42,9 +42,23 @@ def test_config_struct_layout_matches_header():
         line = line.split("/*")[0]
         m = re.match(r"\s*(uint32_t|int32_t|uint64_t|double)\s+([^;]+);", line)
         if m:
-            names += [n.strip() for n in m.group(2).split(",")]
-    from hgaprec_b200.capi import _Config
+            names += [re.sub(r"\[.*\]", "", n).strip() for n in m.group(2).split(",")]
+    from hgaprec_b200.capi import _Config, MAX_DEVICES
     assert [f[0] for f in _Config._fields_] == names
+    assert "#define HPF_MAX_DEVICES %d" % MAX_DEVICES in src and "#define HPF_ABI_VERSION %d" % H.capi.ABI_VERSION in src
+
+
+def test_stats_struct_layout_matches_header():
+    src = open(HEADER).read()
+    body = src[src.index("typedef struct hpf_stats {"):src.index("} hpf_stats;")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        m = re.match(r"\s*(uint32_t|uint64_t|float)\s+(\w+);", line.split("/*")[0])
+        if m:
+            fields.append((m.group(2), m.group(1)))
+    from hgaprec_b200.capi import Stats
+    ctype = {"uint32_t": ctypes.c_uint32, "uint64_t": ctypes.c_uint64, "float": ctypes.c_float}
+    assert [(f[0], f[1]) for f in Stats._fields_] == [(n, ctype[t]) for n, t in fields]
 
 
 def test_no_cpu_fallback_without_cuda():

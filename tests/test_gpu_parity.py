@@ -344,6 +344,30 @@ def test_full_size_netflix_shape_mass_conservation():
     assert np.isfinite(th).all() and np.isfinite(be).all()
 
 
+def test_full_size_netflix_one_iteration_matches_oracle():
+    """BASELINE config C2 at FULL size against the fp64 restatement of the reference loop (all host cores, rows are
+    independent; ~1 minute): one iteration from the reference's own initialize() law, every element of every parameter
+    set under the single-iteration gate of SURVEY.md 8c, and the held-out log-likelihood."""
+    import os
+    c = synth.CONFIGS["netflix"]
+    d = synth.make_ratings(c["n"], c["m"], c["nnz"], seed=c["seed"], heldout=0.002)
+    n, m, k = d["n"], d["m"], 100
+    s = O.OracleState(n, m, k, H.HIER).init(20131104)
+    with make_engine(s) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(1)
+        got = util.pull_state(e, s)
+        hu, hi, hy = d["heldout"]
+        ll = e.heldout_loglik(hu, hi, hy)
+        st = e.stats()
+    want = s.iterate(d["row_ptr"], d["col_idx"], d["y"], 1, nthreads=os.cpu_count() or 1)   # in place: 3 GB of fp64 state
+    assert st["slow_path_nnz"] == 0 and st["head_nnz"] > 0                  # the default plan: dense head + gather tail
+    bad = util.compare_states(got, want)
+    assert not bad, bad
+    assert abs(ll - want.heldout(hu, hi, hy)) / len(hu) <= util.TOL_LL_20IT
+
+
 # ------------------------------------------------ -gen-ranking: scoring + top-N
 def _check_topn(items, scores, o_items, o_scores, m, topn, rel=1e-4):
     """Engine (split-bf16 tensor-core scores, fp32) against the fp64 oracle:

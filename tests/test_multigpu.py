@@ -257,3 +257,49 @@ def test_two_gpu_exact_fallback_is_reduced_over_the_ranks(flags):
     assert out[0][1]["slow_path_nnz"] > 0
     bad = util.compare_states(_stitch(out, s, n, m, k, flags), want, rel=6e-5, elog_abs=6e-5)
     assert not bad, bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [H.HIER, H.BIAS])
+def test_one_ctx_driving_two_gpus_is_bitwise_the_two_rank_run(flags):
+    """hpf_config.n_devices = 2: ONE ctx shards its users over both GPUs (the form the `hgaprec -gpus N` command line
+    uses; SURVEY.md 8b: one process).  Same partition, same kernels, same NCCL sums as two one-device ctxs joined with
+    hpf_comm_init, so the state must be bit-identical; held-out ll, top-N and item ranks take GLOBAL user numbers."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 4000, 1000, 150000, 64, 3
+    d = synth.make_ratings(n, m, nnz, seed=41, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(42)
+    two = _stitch(_run_two_ranks(d, s, flags, iters, k), s, n, m, k, flags)
+    hu, hi, hy = d["heldout"]
+    users = np.array([3, 3999, 1700, 0, 2500, 2100], dtype=np.uint32)          # both shards, arbitrary order
+    rp = d["row_ptr"].astype(np.int64)
+    ep = np.zeros(len(users) + 1, np.uint64)
+    ep[1:] = np.cumsum([rp[u + 1] - rp[u] for u in users])
+    ei = np.concatenate([d["col_idx"][rp[u]:rp[u + 1]] for u in users])
+    qp = np.arange(0, 3 * len(users) + 1, 3, dtype=np.uint64)
+    qi = np.tile(np.array([5, 77, 900], dtype=np.uint32), len(users))
+    with H.Engine(n, m, k, flags=flags, devices=[0, 1]) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(iters)
+        got = util.pull_state(e, s)
+        st = e.stats()
+        ll = e.heldout_loglik(hu, hi, hy)
+        items, scores = e.topn(users, ep, ei, 20)
+        ranks, rscores = e.item_ranks(users, ep, ei, qp, qi)
+    assert st["n_devices"] == 2 and st["nnz"] == len(d["col_idx"])
+    for g in util.groups(s):
+        for f in O.FIELDS:
+            np.testing.assert_array_equal(got.p[g][f], two.p[g][f], err_msg="%s.%s" % (g, f))
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8)
+    assert abs(ll - want.heldout(hu, hi, hy)) / len(hu) <= 2e-4
+    # ranking calls against a single-GPU ctx holding the same state
+    with H.Engine(n, m, k, flags=flags, device=0) as e1:
+        util.push_state(e1, got)
+        items1, scores1 = e1.topn(users, ep, ei, 20)
+        ranks1, rscores1 = e1.item_ranks(users, ep, ei, qp, qi)
+    np.testing.assert_array_equal(items, items1)
+    np.testing.assert_array_equal(scores, scores1)
+    np.testing.assert_array_equal(ranks, ranks1)
+    np.testing.assert_array_equal(rscores, rscores1)

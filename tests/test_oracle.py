@@ -198,10 +198,11 @@ def test_oracle_matches_live_reference_run():
 
 
 # ------------------------------------------------------------------ C1: the real MovieLens-1M fixture, K=100, 20 iterations
-def test_oracle_and_host_reader_pinned_on_movielens_k100_t20(tmp_path):
+def test_oracle_and_host_reader_pinned_on_movielens_k100_t21(tmp_path):
     """BASELINE configs[0]: example/HPF-KDD-movielens.tgz with scripts/run.pl:109-111's flags, -hier, K=100, seed 111.
-    The C++ host reader + start state (hgaprec_hostcheck) on the real files, then the plain-C restatement for 10 and
-    20 iterations (all host cores), against what the UNMODIFIED reference produced (tests/golden/movielens/ref_T20.npz:
+    The C++ host reader + start state (hgaprec_hostcheck) on the real files, then the plain-C restatement for 11 and
+    21 iterations (all host cores; the states the CLI reports as "iteration 10" and "iteration 20": it counts from 0
+    and reports after the update), against what the UNMODIFIED reference produced (tests/golden/movielens/ref_T21.npz:
     fp64 row sums, column sums and 4096 sampled entries of every matrix, its held-out sums).  Generation-time figures
     over the full states: bit-identical single-threaded, 1.6e-8 max rel threaded (oracle_pin.json)."""
     import json
@@ -209,12 +210,12 @@ def test_oracle_and_host_reader_pinned_on_movielens_k100_t20(tmp_path):
     host = os.path.join(ROOT, "hgaprec_b200", "host")
     subprocess.check_call(["make", "-C", host, "../bin/hgaprec_hostcheck"], stdout=subprocess.DEVNULL)
     pin = json.load(open(os.path.join(util.MOVIELENS, "oracle_pin.json")))
-    assert pin["T20_max_rel_oracle_vs_reference_1thread"] == 0.0 and pin["T20_max_rel_oracle_vs_reference_threaded"] < 1e-6
+    assert pin["T21_max_rel_oracle_vs_reference_1thread"] == 0.0 and pin["T21_max_rel_oracle_vs_reference_threaded"] < 1e-6
     data = util.write_movielens(str(tmp_path / "movielens"))
     out = str(tmp_path / "dump.bin")
     subprocess.check_call([os.path.join(ROOT, "hgaprec_b200", "bin", "hgaprec_hostcheck"), "-dir", data, "-out", out] + util.MOVIELENS_FLAGS)
     d = O.read_dump(out)
-    z = np.load(os.path.join(util.MOVIELENS, "ref_T20.npz"))
+    z = np.load(os.path.join(util.MOVIELENS, "ref_T21.npz"))
     # the reader on the real files: same seq numbering, same CSR (checksums), same held-out counts as the reference
     np.testing.assert_array_equal(d["seq2user"], z["seq2user"])
     np.testing.assert_array_equal(d["seq2movie"], z["seq2movie"])
@@ -224,8 +225,8 @@ def test_oracle_and_host_reader_pinned_on_movielens_k100_t20(tmp_path):
     assert len(d["csr.col_idx"]) == pin["nnz_train"] == 792166
     s = O.state_from_dump(dict(d, meta=np.array([6040, 3681, 100, 0, 1, 0, 0, 1], dtype=np.float64)))
     csr = (d["csr.row_ptr"], d["csr.col_idx"], d["csr.y"])
-    for T in (10, 20):
-        s.iterate(*csr, 10, nthreads=os.cpu_count() or 1)
+    for T in (11, 21):
+        s.iterate(*csr, 11 if T == 11 else 10, nthreads=os.cpu_count() or 1)
         fp = util.fingerprint(s)
         for key, val in fp.items():
             ref = z["T%d/fp/%s" % (T, key)]
@@ -236,6 +237,7 @@ def test_oracle_and_host_reader_pinned_on_movielens_k100_t20(tmp_path):
         for split in ("validation", "test"):
             ll = s.heldout(d[split + ".u"], d[split + ".i"], d[split + ".y"])
             assert abs(ll - float(z["T%d/%s.ll_sum" % (T, split)][0])) <= 1e-6 * abs(ll), (T, split)
-    # and the reference CLI's own report agrees with its harness dump (validation.txt row of iteration 20)
+    # and the reference CLI's own report agrees with its harness dump (validation.txt row of iteration 20 = 21 sweeps)
     row = open(os.path.join(util.MOVIELENS, "cli", "validation.txt")).read().splitlines()[-1].split("\t")
     assert int(row[0]) == 20 and int(row[3]) == 8001
+    assert abs(float(row[2]) - float(z["T21/validation.ll_sum"][0]) / 8001) <= 1e-8
