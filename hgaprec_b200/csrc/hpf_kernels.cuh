@@ -32,9 +32,6 @@ constexpr int kSweepThreads = 256;
 #ifndef HPF_SWEEP_MINBLOCKS
 #define HPF_SWEEP_MINBLOCKS 3
 #endif
-#ifndef HPF_SWEEP_PIPE
-#define HPF_SWEEP_PIPE 1   // software-pipelined gather loop (0: the round-1 loop, kept for A/B timing)
-#endif
 #define HPF_PRAGMA(x) _Pragma(#x)
 #define HPF_UNROLL(n) HPF_PRAGMA(unroll n)
 constexpr int kUpdateWarps = 8;
@@ -264,66 +261,11 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
   // never stored), so the loop carries no predicates.  Only the last of the V slots can be out of range.
   const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
 
-  if constexpr (HPF_SWEEP_PIPE != 0 && G >= 2) {
-  // Software pipeline: the gathered row of nonzero j + 1 is requested BEFORE the arithmetic of nonzero j (two row
-  // buffers, the loop unrolled by two so that no buffer is ever copied), and the (index, rating) pair of chunk
-  // c + 1 before chunk c is walked.  A warp issues in order, so without this its loads and its dependent
-  // dot -> shuffle -> rcp -> axpy chain alternate instead of overlapping (measured: tools/gather_bench.cu reaches
-  // 22 TB/s with this access pattern where the unpipelined loop stops at 12.5).
-  auto fetch_pair = [&](uint32_t j0, uint32_t &cb, float &yb) {
-    const uint32_t jj = j0 + gl;
-    cb = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row
-    yb = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f; // 0: no contribution
-  };
-  auto fetch_row = [&](uint32_t c, float4 (&b)[V], float2 &caux) {
-    const float4 *cp = acol + (size_t)c * a.ld4;
-#pragma unroll
-    for (int v = 0; v < V - 1; ++v) b[v] = ldg4(cp + gl + v * G);
-    b[V - 1] = ldg4(cp + q_last);
-    if (BIAS) caux = __ldg(a.col_aux + c);
-  };
-  auto consume = [&](uint32_t c, float yv, const float4 (&b)[V], const float2 caux) {
-    float dot = dot_rows<V>(ar, b);
-#pragma unroll
-    for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    float z = dot;
-    if (BIAS) z += raux.x * caux.y + caux.x * raux.y;
-    const bool ok = z > kZMin && z < kZMax;
-    const float sc = ok ? yv * frcp(z) : 0.f;
-    axpy_rows<V>(sc, b, acc);
-    if (BIAS) accb = fmaf(sc, caux.y, accb);
-    if (!ok && yv != 0.f) { // Z left the fp32 range: exact log-domain path (rare)
-      SlowArgs sa;
-      sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
-      sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
-      sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
-      sweep_slow_path<G, V, BIAS>(sa, row, c, yv, lane);
-    }
-  };
-  uint32_t cbuf, cnext = 0u;
-  float ybuf, ynext = 0.f;
-  fetch_pair(0, cbuf, ybuf);
-  float4 b0[V], b1[V];
-  float2 x0 = make_float2(0.f, 0.f), x1 = make_float2(0.f, 0.f);
-  uint32_t c0 = __shfl_sync(0xffffffffu, cbuf, 0, G), c1;
-  fetch_row(c0, b0, x0);
-  for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
-    if (j0 + G < maxlen) fetch_pair(j0 + G, cnext, ynext); // warp-uniform: maxlen is the warp's maximum
-    else { cnext = 0u; ynext = 0.f; }
-#pragma unroll
-    for (int t = 0; t < G; t += 2) {
-      c1 = __shfl_sync(0xffffffffu, cbuf, t + 1, G);
-      fetch_row(c1, b1, x1);
-      consume(c0, __shfl_sync(0xffffffffu, ybuf, t, G), b0, x0);
-      c0 = t + 2 < G ? __shfl_sync(0xffffffffu, cbuf, (t + 2) & (G - 1), G) : __shfl_sync(0xffffffffu, cnext, 0, G);
-      fetch_row(c0, b0, x0); // past the last chunk: row 0, never consumed
-      consume(c1, __shfl_sync(0xffffffffu, ybuf, t + 1, G), b1, x1);
-    }
-    cbuf = cnext; ybuf = ynext;
-  }
-  } else {
-  // chunks of G nonzeros: every lane of the group fetches one (index, rating), then the chunk is unrolled
-  // so that the gathers of one nonzero overlap the arithmetic of the previous one
+  // chunks of G nonzeros: every lane of the group fetches one (index, rating), then walks the chunk.  The loop is
+  // deliberately NOT software-pipelined: the kernel sits at the practical ceiling of the L1 data pipe (4 wavefronts per
+  // gathered 512-byte row + 1.25 for the shuffles; ncu lsu write-back ~60 % busy, the same as the pure-gather
+  // micro-benchmark at its 22 TB/s peak), and prefetching the next row only costs registers and occupancy
+  // (measured 10-65 % slower: profiles/r02d_sweep_pipeline_experiment.txt)
   for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
     const uint32_t jj = j0 + gl;
     const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row
@@ -358,7 +300,6 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
         sweep_slow_path<G, V, BIAS>(sa, row, c, yv, lane);
       }
     }
-  }
   }
 
   if (have) {

@@ -14,9 +14,13 @@
 // K columns ([.., bias_u, 1] . [.., 1, bias_i]).
 //
 // One CTA owns 128 users (the UMMA M) and streams all items in tiles of 256 (the
-// UMMA N), double-buffered in TMEM (2 x 256 columns):
+// UMMA N).  The kernel is bound by its epilogue (selection), not by the tensor
+// pipe (3 x 1.7 TFLOP = 3.6 ms of MMA at C5), so a CTA is kept SMALL -- one 96 KB
+// operand stage, one 256-column accumulator -- and TWO CTAs share an SM: while one
+// drains its accumulator the other one's MMAs run, and eight epilogue warps
+// instead of four hide each other's latencies:
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D, 128B-swizzled K-major
-//               boxes of the hi / lo operand matrices into a 2-stage smem ring
+//               boxes of the hi / lo operand matrices into the operand stage
 //   warp 1      TMEM allocator + the single thread that issues tcgen05.mma
 //   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, one THREAD per user
 //               row; a score is kept only if it beats the row's running
@@ -24,7 +28,8 @@
 //               Netflix-scale problem are never materialised.  Survivors go to
 //               a per-row candidate buffer in global memory (L2 resident); when
 //               a buffer runs full the warp selects the topn-th largest key with
-//               a bitwise count-select in registers and compacts.
+//               an 8-bit MSB-first radix select (histogram in shared memory)
+//               and compacts.
 // Keys are 64 bit, (score bits << 32) | ~item: scores are >= 0 so the float bits
 // order like the values, all keys are distinct, and "larger key" is exactly
 // "higher score, ties by lower item" (the reference's qsort is unstable on ties;
@@ -41,7 +46,8 @@ namespace topk {
 constexpr int kTileM = 128;        // users per CTA == UMMA M
 constexpr int kTileN = 256;        // items per accumulator buffer == UMMA N
 constexpr int kBlockK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int kStages = 2;
+constexpr int kStages = 1;
+constexpr uint32_t kTmemCols = 256; // one accumulator tile: two CTAs per SM share the 512 TMEM columns
 constexpr int kCap = 512;          // candidate slots per user row
 constexpr int kMaxTopN = 256;      // kCap - kTileN
 constexpr int kThreads = 192;      // 6 warps
@@ -49,7 +55,8 @@ constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KB per (hi | lo) box
 constexpr uint32_t kBBytes = kTileN * kBlockK * 2;  // 32 KB
 constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes; // 96 KB
 constexpr uint32_t kSortBytes = 4 * kMaxTopN * 8;   // final sort buffers, one per epilogue warp
-constexpr uint32_t kSmemBytes = 1024 + kStages * kStageBytes + kSortBytes + 256;
+constexpr uint32_t kHistBytes = 4 * 256 * 4;        // radix-select histograms, one per epilogue warp
+constexpr uint32_t kSmemBytes = 1024 + kStages * kStageBytes + kSortBytes + kHistBytes + 256; // 111,872: two per SM
 constexpr unsigned long long kSpinLimit = 1ull << 28;
 
 // ---- PTX wrappers -----------------------------------------------------------
@@ -80,6 +87,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         : "r"(bar), "r"(parity)
         : "memory");
     if (spin > kSpinLimit) __trap();
+  }
+}
+// the same for the two single-thread roles (TMA producer, MMA issuer): they wait for most of the kernel's life and
+// would otherwise spend a fifth of the SM's issue slots on the polling loop (ncu, round 1)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+  uint32_t done = 0;
+  for (unsigned long long spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(64);
+    if (spin > (kSpinLimit >> 4)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
@@ -203,91 +227,108 @@ __device__ __forceinline__ bool is_excluded(const uint32_t *lst, uint32_t len, u
 
 // Warp-cooperative: among the cnt (<= kCap) keys of one row keep the `keep`
 // largest (keep <= cnt), compacted to the front of buf in arbitrary order;
-// returns the smallest kept key (the row's new threshold).  Keys are distinct.
-// The keep-th largest key is found by a bitwise count-select in registers: first
-// on the score word (32-bit compares), then -- only among the keys that tie on
-// it -- on the item word.
-__device__ __forceinline__ unsigned long long warp_select(unsigned long long *buf, uint32_t cnt, uint32_t keep, int lane)
+// returns the smallest kept key (the row's new threshold).  Keys are distinct
+// and nonzero.  The keep-th largest key is found by an MSB-first radix select, 8
+// bits per pass, over the 64-bit keys held in registers (kCap / 32 per lane):
+// a 256-bin histogram of the keys still in play (shared memory atomics), a
+// descending scan of the bins (8 per lane + a warp scan), the bin that holds the
+// keep-th key narrows the prefix.  Leading bytes on which all keys agree are
+// skipped, and the search stops as soon as the chosen bin holds exactly the keys
+// still needed, so a typical call takes 2-3 passes (scores differ within their
+// upper three bytes) instead of the ~40 bit steps of a bitwise count-select.
+__device__ __forceinline__ unsigned long long warp_select(unsigned long long *buf, uint32_t cnt, uint32_t keep, int lane, uint32_t *hist)
 {
   constexpr int PER = kCap / 32;
-  uint32_t hi[PER], lo[PER];
-  uint32_t hor = 0u, hand = 0xffffffffu;
+  unsigned long long key[PER];
+  unsigned long long kor = 0ull, kand = ~0ull;
 #pragma unroll
   for (int t = 0; t < PER; ++t) {
     const uint32_t j = lane + 32 * t;
-    const unsigned long long k = j < cnt ? buf[j] : 0ull; // 0 is not a real key (that would be item 2^32-1)
-    hi[t] = (uint32_t)(k >> 32);
-    lo[t] = (uint32_t)k;
-    if (j < cnt) { hor |= hi[t]; hand &= hi[t]; }
+    key[t] = j < cnt ? buf[j] : 0ull; // 0 is not a real key (that would be item 2^32-1)
+    if (j < cnt) { kor |= key[t]; kand &= key[t]; }
   }
-  hor = __reduce_or_sync(0xffffffffu, hor);
-  hand = __reduce_and_sync(0xffffffffu, hand);
-  // largest T with count(hi >= T) >= keep, scanning only the bits on which the scores differ
-  uint32_t thr = hand;
-  for (uint32_t vary = hor & ~hand; vary != 0u;) {
-    const uint32_t b = 31u - (uint32_t)__clz(vary);
-    vary &= ~(1u << b);
-    const uint32_t trial = thr | (1u << b);
-    uint32_t c = 0;
-#pragma unroll
-    for (int t = 0; t < PER; ++t) c += (hi[t] >= trial && lo[t] != 0u) ? 1u : 0u;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= keep) thr = trial;
-  }
-  // keys with a larger score word are all kept; among those that tie on it, the `need` largest item words
-  uint32_t above = 0, ties = 0;
-#pragma unroll
-  for (int t = 0; t < PER; ++t) {
-    const bool real = lo[t] != 0u;
-    above += (real && hi[t] > thr) ? 1u : 0u;
-    ties += (real && hi[t] == thr) ? 1u : 0u;
-  }
-  above = __reduce_add_sync(0xffffffffu, above);
-  ties = __reduce_add_sync(0xffffffffu, ties);
-  const uint32_t need = keep - above; // 1 <= need <= ties
-  uint32_t lthr = 0u;                  // smallest kept item word among the ties
-  if (need < ties) {
-    uint32_t lor = 0u, land = 0xffffffffu;
+  kor = ((unsigned long long)__reduce_or_sync(0xffffffffu, (uint32_t)(kor >> 32)) << 32) | __reduce_or_sync(0xffffffffu, (uint32_t)kor);
+  kand = ((unsigned long long)__reduce_and_sync(0xffffffffu, (uint32_t)(kand >> 32)) << 32) | __reduce_and_sync(0xffffffffu, (uint32_t)kand);
+  unsigned long long thr = 0ull;  // the keep-th largest key
+  if (keep == cnt) {               // everything stays: the threshold is the smallest key
+    unsigned long long mn = ~0ull;
 #pragma unroll
     for (int t = 0; t < PER; ++t)
-      if (lo[t] != 0u && hi[t] == thr) { lor |= lo[t]; land &= lo[t]; }
-    lor = __reduce_or_sync(0xffffffffu, lor);
-    land = __reduce_and_sync(0xffffffffu, land);
-    lthr = land;
-    for (uint32_t vary = lor & ~land; vary != 0u;) {
-      const uint32_t b = 31u - (uint32_t)__clz(vary);
-      vary &= ~(1u << b);
-      const uint32_t trial = lthr | (1u << b);
-      uint32_t c = 0;
+      if (key[t] != 0ull && key[t] < mn) mn = key[t];
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, (uint32_t)(mn >> 32));
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, (uint32_t)(mn >> 32) == mh ? (uint32_t)mn : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+  }
+  const unsigned long long vary = kor & ~kand;
+  int shift = vary == 0ull ? 0 : (63 - __clzll((long long)vary)) & ~7; // first byte on which the keys differ
+  unsigned long long prefix = shift >= 56 ? 0ull : (kand >> (shift + 8)) << (shift + 8);
+  unsigned long long pmask = shift >= 56 ? 0ull : ~0ull << (shift + 8);
+  uint32_t need = keep;            // the answer is the need-th largest of the keys matching the prefix
+  for (;; shift -= 8) {
 #pragma unroll
-      for (int t = 0; t < PER; ++t) c += (hi[t] == thr && lo[t] >= trial) ? 1u : 0u;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= need) lthr = trial;
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < PER; ++t)
+      if (key[t] != 0ull && (key[t] & pmask) == prefix) atomicAdd(hist + (uint32_t)((key[t] >> shift) & 255ull), 1u);
+    __syncwarp();
+    // lane L owns the digits 255 - 8L ... 248 - 8L, i.e. bins in DESCENDING digit order across the warp
+    uint32_t h[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[i] = hist[255 - (8 * lane + i)]; sum += h[i]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
     }
-  } else {
-    uint32_t lmin = 0xffffffffu;
+    const uint32_t excl = incl - sum;
+    const bool mine = excl < need && need <= incl; // exactly one lane
+    uint32_t digit = 0, left = 0, inbin = 0;
+    if (mine) {
+      uint32_t run = excl;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (inbin == 0u && run + h[i] >= need) { digit = 255u - (uint32_t)(8 * lane + i); left = need - run; inbin = h[i]; }
+        run += h[i];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    digit = __shfl_sync(0xffffffffu, digit, src);
+    need = __shfl_sync(0xffffffffu, left, src);
+    inbin = __shfl_sync(0xffffffffu, inbin, src);
+    prefix |= (unsigned long long)digit << shift;
+    pmask |= 255ull << shift;
+    if (inbin == need || shift == 0) break; // every key of the bin is kept (or the key is fully determined)
+  }
+  // threshold: the smallest key matching the prefix (all of them are kept when the loop stopped on inbin == need;
+  // with shift == 0 the prefix IS the key)
+  {
+    unsigned long long mn = ~0ull;
 #pragma unroll
     for (int t = 0; t < PER; ++t)
-      if (lo[t] != 0u && hi[t] == thr) lmin = min(lmin, lo[t]);
-    lthr = __reduce_min_sync(0xffffffffu, lmin);
+      if (key[t] != 0ull && (key[t] & pmask) == prefix && key[t] < mn) mn = key[t];
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, (uint32_t)(mn >> 32));
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, (uint32_t)(mn >> 32) == mh ? (uint32_t)mn : 0xffffffffu);
+    thr = ((unsigned long long)mh << 32) | ml;
   }
   // compact: kept keys to the front (each lane writes its own, offsets by warp scan)
-  uint32_t mine = 0;
+  uint32_t mine_cnt = 0;
 #pragma unroll
-  for (int t = 0; t < PER; ++t) mine += (lo[t] != 0u && (hi[t] > thr || (hi[t] == thr && lo[t] >= lthr))) ? 1u : 0u;
-  uint32_t incl = mine;
+  for (int t = 0; t < PER; ++t) mine_cnt += (key[t] >= thr && key[t] != 0ull) ? 1u : 0u;
+  uint32_t incl = mine_cnt;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
     if (lane >= off) incl += v;
   }
-  uint32_t pos = incl - mine;
+  uint32_t pos = incl - mine_cnt;
   __syncwarp();
 #pragma unroll
   for (int t = 0; t < PER; ++t)
-    if (lo[t] != 0u && (hi[t] > thr || (hi[t] == thr && lo[t] >= lthr))) buf[pos++] = ((unsigned long long)hi[t] << 32) | lo[t];
+    if (key[t] >= thr && key[t] != 0ull) buf[pos++] = key[t];
   __syncwarp();
-  return ((unsigned long long)thr << 32) | lthr;
+  return thr;
 }
 
 // bitonic sort (descending) of P = 2^p <= kMaxTopN keys in shared memory by one warp

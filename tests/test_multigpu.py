@@ -251,6 +251,9 @@ def test_two_gpu_exact_fallback_is_reduced_over_the_ranks(flags):
     s = O.OracleState(n, m, k, flags).init(6)
     s.p["theta"]["Elogv"][:, 1:] -= 200.0
     s.p["beta"]["Elogv"][:, :-1] -= 200.0
+    if flags & H.BIAS:   # the two bias slots of phi must not rescue the normaliser
+        s.p["thetabias"]["Elogv"] -= 300.0
+        s.p["betabias"]["Elogv"] -= 300.0
     want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters)
     out = _run_two_ranks(d, s, flags, iters, k)
     assert out[0][1]["mg_exact"] == 1 and out[1][1]["mg_exact"] == 1
