@@ -187,7 +187,7 @@ struct hpf_ctx {
   size_t csr_idx_cap = 0, csr_y_cap = 0, csc_idx_cap = 0, csc_y_cap = 0, upass_idx_cap = 0, upass_y_cap = 0;
   Arena dev_arena, pin_arena;    // grow-only device / pinned-host scratch of hpf_set_ratings_csr
   DensePlan dense;               // the most popular items as a dense block on the tensor cores
-  double dense_block_share = 0.06; // HPF_DENSE_BLOCK_SHARE: minimum share of the nonzeros for a 2nd..4th head block
+  double dense_block_share = -1.0; // HPF_DENSE_BLOCK_SHARE: minimum share of the nonzeros for a 2nd..4th head block (< 0: the cost model in hpf_set_ratings_csr)
   int head_variant = 7;          // HPF_HEAD_VARIANT: epilogue organisation of head_kernel (hpf_head.cuh); 7 measured fastest (profiles/r02b_exp_head_variants.log)
   int dense_head_mode = -1;      // HPF_DENSE_HEAD: -1 auto (on when the head carries >= 15 % of the nonzeros), 0 off, 1 forced
   uint32_t *tail_idx = nullptr; uint8_t *tail_y = nullptr; size_t tail_idx_cap = 0, tail_y_cap = 0; // user-pass tail CSR
@@ -1217,8 +1217,13 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   }
 
   // ================= decision: dense head on the tensor cores =================
-  // blocks of 128 items by descending popularity: the first must carry >= 15 % of the nonzeros, every further
-  // one >= 6 % (a block costs one dense pass over all users whatever its density; measured break-even ~6 %)
+  // blocks of 128 items by descending popularity.  The first must carry >= 15 % of the nonzeros.  Every further one
+  // must pay for itself: a block costs one dense pass over ALL local users whatever its density -- measured ~9.8 us
+  // per wave of user tiles (one tile of 128 users per SM) plus ~30 us of fixed cost (three launches, operand split,
+  // TMEM / B_head prologue) -- and saves ~6.6e-8 ms of gathers per nonzero over the two passes (Netflix scale: 5.36 /
+  // 5.24 / 5.23 ms per iteration with 2 / 3 / 4 blocks, profiles/r02f_exp_block_share.log; with the users spread over 8
+  // GPUs the fixed part dominates and two blocks are right).  HPF_DENSE_BLOCK_SHARE overrides the model with a
+  // plain minimum share of the nonzeros.
   bool dense_head = false;
   uint32_t H = 0;
   uint64_t head_nnz = 0;
@@ -1227,8 +1232,10 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     for (uint32_t b = 0; b < kMaxHeadBlocks && b * head::kHead < m; ++b) {
       uint64_t blk = 0;
       for (uint32_t r = b * head::kHead; r < std::min<uint32_t>((b + 1) * head::kHead, m); ++r) blk += 0xffffffffu - h_degkey[r];
-      const bool take = b == 0 ? (c->dense_head_mode == 1 || (double)blk >= 0.15 * (double)nnz)
-                               : ((double)blk >= c->dense_block_share * (double)nnz);
+      const double waves = std::ceil((double)((n + head::kUsers - 1) / head::kUsers) / (double)c->sm_count);
+      const bool pays = c->dense_block_share >= 0.0 ? (double)blk >= c->dense_block_share * (double)nnz
+                                                    : (double)blk * 6.6e-8 > 0.030 + 0.0098 * waves;
+      const bool take = b == 0 ? (c->dense_head_mode == 1 || (double)blk >= 0.15 * (double)nnz) : pays;
       if (!take) break;
       head_nnz += blk;
       nblk = b + 1;
@@ -1880,24 +1887,53 @@ int hpf_item_ranks(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_
     CU(cudaStreamSynchronize(c->stream));
     if (bad != 0) return fail(c, HPF_EINVAL, "excl_idx holds item %u >= n_items=%u", bad, m);
   }
+  // operands of the tensor-core scoring pass, as in hpf_topn: hi / lo split of E[beta] (+ {1, E[betabias]}) and of the
+  // listed users' E[theta] rows (+ {E[thetabias], 1})
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensormap_encoder();
+  if (!encode) return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const uint32_t Kext = c->K + (c->bias ? 2u : 0u);
+  const uint32_t Kpad = (Kext + topk::kBlockK - 1) / topk::kBlockK * topk::kBlockK;
+  const uint32_t m_pad = (m + topk::kTileN - 1) / topk::kTileN * topk::kTileN;
+  const uint32_t nu_pad = (nu + topk::kTileM - 1) / topk::kTileM * topk::kTileM;
+  __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  CU(tmp.get(&a_hi, (size_t)nu_pad * Kpad)); CU(tmp.get(&a_lo, (size_t)nu_pad * Kpad));
+  CU(tmp.get(&b_hi, (size_t)m_pad * Kpad)); CU(tmp.get(&b_lo, (size_t)m_pad * Kpad));
+  topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->be.Ev, c->ld, c->K, c->bias ? c->be.b_Ev : nullptr, 0, nullptr, m, m_pad,
+                                                         Kpad, b_hi, b_lo);
+  topk::split_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->th.Ev, c->ld, c->K, c->bias ? c->th.b_Ev : nullptr, 1, d_users, nu, nu_pad,
+                                                         Kpad, a_hi, a_lo);
+  c->launches += 2;
+  auto make_map = [&](CUtensorMap *map, void *ptr, uint64_t rows, uint32_t box_rows) -> bool {
+    cuuint64_t dims[2] = { Kpad, rows };
+    cuuint64_t strides[1] = { (cuuint64_t)Kpad * 2 };
+    cuuint32_t box[2] = { (cuuint32_t)topk::kBlockK, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  if (!make_map(&map_a_hi, a_hi, nu_pad, topk::kTileM) || !make_map(&map_a_lo, a_lo, nu_pad, topk::kTileM) ||
+      !make_map(&map_b_hi, b_hi, m_pad, topk::kTileN) || !make_map(&map_b_lo, b_lo, m_pad, topk::kTileN))
+    return fail(c, HPF_ECUDA, "cuTensorMapEncodeTiled failed for the ranking operands");
   topk::RankArgs a;
   a.nu = nu; a.m = m; a.K = c->K; a.ld = c->ld;
-  const size_t fixed = (size_t)topk::kRankWarps * c->K * 4;
-  uint32_t chunk = 64;
-  while (chunk > 32 && fixed + (size_t)chunk * ((c->K + 1) * 4 + topk::kRankWarps * 8) > (160u << 10)) chunk -= 32;
-  a.chunk = chunk;
+  a.nkb = Kpad / topk::kBlockK; a.ntiles_n = m_pad / topk::kTileN;
   a.users = d_users; a.Et = c->th.Ev; a.Eb = c->be.Ev;
   a.Etb = c->bias ? c->th.b_Ev : nullptr; a.Ebb = c->bias ? c->be.b_Ev : nullptr;
   a.excl_ptr = d_exptr; a.excl_sorted = d_exidx; a.q_ptr = d_qptr; a.q_idx = d_qidx; a.q_key = d_qkey;
   a.rank_out = d_rank; a.score_out = d_score;
-  const size_t smem = fixed + (size_t)chunk * ((c->K + 1) * 4 + topk::kRankWarps * 8) + 16;
-  CU(cudaFuncSetAttribute(topk::rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk::rank_kernel<<<(nu + topk::kRankWarps - 1) / topk::kRankWarps, topk::kRankWarps * 32, smem, c->stream>>>(a);
-  c->launches++;
+  // the queries' own keys (fp32 dot products: the scores handed back), then the counting pass on the tensor cores
+  topk::rank_prep_kernel<<<(nu + topk::kRankWarps - 1) / topk::kRankWarps, topk::kRankWarps * 32, (size_t)topk::kRankWarps * c->K * 4, c->stream>>>(a);
+  CU(cudaFuncSetAttribute(topk::rank_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk::kRankSmemBytes));
+  CU(cudaEventRecord(c->ev0, c->stream));
+  topk::rank_mma_kernel<<<nu_pad / topk::kTileM, topk::kRankThreads, topk::kRankSmemBytes, c->stream>>>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, a);
+  CU(cudaEventRecord(c->ev1, c->stream));
+  c->launches += 2;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(rank_out, d_rank, nq * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(score_out, d_score, nq * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&c->last_topn_ms, c->ev0, c->ev1));
   return 0;
 }
 

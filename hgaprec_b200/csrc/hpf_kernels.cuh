@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const uint32_t q = gl + v * G;
-      ar[v] = (have && q < a.K4) ? ldg4(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ar[v] = (have && len > 0u && q < a.K4) ? ldg4(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f); // an empty row only clears its T row
       acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -270,8 +270,12 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
     const uint32_t jj = j0 + gl;
     const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row
     const float ybuf = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f; // 0: no contribution
+    // the last chunk of the warp's longest segment may be short: walk only what exists (warp-uniform bound).  With
+    // users sharded over GPUs most item rows hold a handful of local nonzeros, and a full chunk would gather row 0
+    // for every missing one.
+    const int tmax = (int)min((uint32_t)G, maxlen - j0);
     HPF_UNROLL(HPF_UNROLL_T)
-    for (int t = 0; t < G; ++t) {
+    for (int t = 0; t < tmax; ++t) {
       const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
       const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
       float4 b[V];

@@ -348,7 +348,7 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long *s, uint32_t P
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const TopnArgs a)
 {
@@ -356,12 +356,13 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sort_off = kStages * kStageBytes;
-  const uint32_t bar_off = sort_off + kSortBytes;
+  const uint32_t hist_off = sort_off + kSortBytes;
+  const uint32_t bar_off = hist_off + kHistBytes;
   const uint32_t bar_full = base + bar_off;            // [kStages]
   const uint32_t bar_empty = bar_full + 8 * kStages;   // [kStages]
-  const uint32_t bar_tfull = bar_empty + 8 * kStages;  // [2]
-  const uint32_t bar_tempty = bar_tfull + 16;          // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + bar_off + 8 * (2 * kStages + 4));
+  const uint32_t bar_tfull = bar_empty + 8 * kStages;  // accumulator complete
+  const uint32_t bar_tempty = bar_tfull + 8;           // accumulator drained
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + bar_off + 8 * (2 * kStages + 2));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tile_m = blockIdx.x;
@@ -371,14 +372,12 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 128);
-    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) { // TMEM: all 512 columns (two 256-column accumulators); this warp also frees them
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+  if (warp == 1) { // TMEM: one 256-column accumulator (the SM's other CTA takes the other half); this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -393,7 +392,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       for (uint32_t j = 0; j < a.ntiles_n; ++j)
         for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_wait_relaxed(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t st = base + s * kStageBytes;
           mbar_expect_tx(bar_full + 8 * s, kStageBytes);
           tma_load_2d(st, &map_a_hi, bar_full + 8 * s, (int)(kb * kBlockK), (int)(tile_m * kTileM));
@@ -407,13 +406,12 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;
       for (uint32_t j = 0; j < a.ntiles_n; ++j) {
-        const uint32_t buf = j & 1u, tph = (j >> 1) & 1u;
-        mbar_wait(bar_tempty + 8 * buf, tph ^ 1u); // epilogue has drained this accumulator
+        mbar_wait_relaxed(bar_tempty, (j & 1u) ^ 1u); // epilogue has drained the accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * (uint32_t)kTileN;
+        const uint32_t d_tmem = tmem_base;
         for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
+          mbar_wait_relaxed(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t st = base + s * kStageBytes;
           const uint64_t da_hi = make_desc_sw128(st), da_lo = make_desc_sw128(st + kABytes);
@@ -427,7 +425,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
           }
           tc_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs have read it
         }
-        tc_commit(bar_tfull + 8 * buf);  // accumulator complete
+        tc_commit(bar_tfull);  // accumulator complete
       }
     }
   } else {
@@ -447,8 +445,8 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     uint32_t tau_hi = live ? 0u : 0xffffffffu;     // score word of the row's threshold: smaller scores cannot make the top-n
     uint32_t cnt = 0;
     uint32_t excur = 0;                            // cursor into the (ascending) exclusion list
+    uint32_t *hist = reinterpret_cast<uint32_t *>(gen_base + hist_off) + (size_t)q * 256;
     for (uint32_t j = 0; j < a.ntiles_n; ++j) {
-      const uint32_t buf = j & 1u, tph = (j >> 1) & 1u;
       const uint32_t col0 = j * kTileN;
       const uint32_t ncols = a.m - col0 < (uint32_t)kTileN ? a.m - col0 : (uint32_t)kTileN;
       // this tile's excluded columns as a 256-bit mask: the list is sorted, so a cursor walks it once per row
@@ -463,12 +461,12 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         for (int w = 0; w < kTileN / 32; ++w) mask[w] |= ((o >> 5) == (uint32_t)w) ? bit : 0u;
         ++excur;
       }
-      mbar_wait(bar_tfull + 8 * buf, tph);
+      mbar_wait(bar_tfull, j & 1u);
       tc_fence_after();
 #pragma unroll
       for (uint32_t c = 0; c < kTileN / 32; ++c) {
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + c * 32, r);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
         tc_wait_ld();
         const uint32_t valid = ncols > c * 32 ? ncols - c * 32 : 0u;
         const uint32_t mw = mask[c];                                   // excluded columns of this chunk
@@ -490,7 +488,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);
+      mbar_arrive(bar_tempty);
       // rows that could overflow during the next tile are pruned now, warp-cooperatively
       __syncwarp();
       uint32_t need = __ballot_sync(0xffffffffu, cnt > (uint32_t)(kCap - kTileN));
@@ -500,7 +498,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
         const uint32_t rcnt = __shfl_sync(0xffffffffu, cnt, src);
         unsigned long long *rb = a.cand + (size_t)(tile_m * kTileM + q * 32 + src) * kCap;
         const uint32_t keep = rcnt < a.topn ? rcnt : a.topn;
-        const unsigned long long thr = warp_select(rb, rcnt, keep, lane);
+        const unsigned long long thr = warp_select(rb, rcnt, keep, lane, hist);
         if (lane == src) {
           cnt = keep;
           if (rcnt >= a.topn) tau_hi = (uint32_t)(thr >> 32);
@@ -518,7 +516,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
       const uint32_t rcnt = __shfl_sync(0xffffffffu, cnt, src);
       unsigned long long *rb = a.cand + (size_t)r_row * kCap;
       const uint32_t keep = rcnt < a.topn ? rcnt : a.topn;
-      if (rcnt > keep) warp_select(rb, rcnt, keep, lane);
+      if (rcnt > keep) warp_select(rb, rcnt, keep, lane, hist);
       for (uint32_t i = lane; i < P; i += 32) sbuf[i] = i < keep ? rb[i] : 0ull;
       __syncwarp();
       warp_sort_desc(sbuf, P, lane);
@@ -536,7 +534,7 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -544,17 +542,35 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 // Item ranks (compute_itemrank, hgaprec.cc:1607-1701): for listed (user, query
 // item) pairs, the position of the item in the user's FULL descending list (same
 // scores, same exclusion rule and same tie order as the top-N: key = score bits,
-// ~item).  position = number of items whose key is larger.  Plain fp32 CUDA-core
-// kernel: one warp per user, 8 users per CTA share each staged chunk of item
-// rows; every score is produced by ONE routine in ONE order, so a query's own key
-// compares equal to itself exactly.  Sized for the report-window use of the
-// reference (thousands of test users); the C5-scale version belongs on the tensor
-// cores next to topn_kernel.
+// ~item).  position = number of OTHER items whose key is larger.
+//
+// Two kernels.  rank_prep_kernel (one warp per user): the queries' own keys from
+// fp32 dot products -- the score the caller gets back.  rank_mma_kernel: the same
+// TMA / tcgen05 scoring pipeline as topn_kernel (all items of 128 users per CTA,
+// 3 x bf16 split), with a COUNTING epilogue instead of a selecting one.  A row's
+// queries are handled 32 at a time: their keys are sorted (ascending) into shared
+// memory, and every score of the row is located among them by a 5-step branch-
+// free binary search, b = #{queries with a smaller key}, and counted in hist[b];
+// afterwards rank_j = sum_{b > j} hist[b].  A row with more than 32 queries takes
+// more passes over the items (the contraction is cheap: the kernel is bound by
+// this epilogue).  The query item meets ITSELF in the stream with the tensor-core
+// score, which need not equal its fp32 key bit for bit; it is recognised by its
+// item id next to the insertion point and taken out of its own count.
+// Shared-memory tables are laid out [slot][row] so that the 32 rows of a warp hit
+// 32 different banks whatever slot each one reads.
 // ---------------------------------------------------------------------------
-constexpr int kRankWarps = 8;
+constexpr int kRankWarps = 8;          // rank_prep_kernel: users per CTA
+constexpr int kQBatch = 32;            // queries of a row per pass
+constexpr int kRankEpiWarps = 8;       // rank_mma_kernel: two epilogue threads per row, half of a tile's columns each
+constexpr int kRankThreads = 64 + 32 * kRankEpiWarps;
+constexpr uint32_t kRankKeyBytes = kQBatch * kTileM * 8;         // sorted query keys      [slot][row]
+constexpr uint32_t kRankHistBytes = (kQBatch + 1) * kTileM * 4;  // counts per bucket      [bucket][row]
+constexpr uint32_t kRankOrigBytes = kQBatch * kTileM;            // query index in the batch, self flag: [slot][row] bytes
+constexpr uint32_t kRankSmemBytes = 1024 + kStageBytes + kRankKeyBytes + kRankHistBytes + 2 * kRankOrigBytes + 256;
 
 struct RankArgs {
-  uint32_t nu, m, K, ld, chunk; // chunk: item rows staged per step (multiple of 32)
+  uint32_t nu, m, K, ld;
+  uint32_t nkb, ntiles_n;           // rank_mma_kernel: K blocks of 64, item tiles of 256
   const uint32_t *users;
   const float *Et, *Eb, *Etb, *Ebb; // E[theta], E[beta] (row stride ld), bias expectations or nullptr
   const uint64_t *excl_ptr; const uint32_t *excl_sorted;
@@ -570,25 +586,20 @@ __device__ __forceinline__ float rank_dot(const float *th, const float *be, uint
   return s;
 }
 
-__global__ void __launch_bounds__(kRankWarps * 32) rank_kernel(const RankArgs a)
+__global__ void __launch_bounds__(kRankWarps * 32) rank_prep_kernel(const RankArgs a)
 {
-  extern __shared__ float rsm[];
-  float *th_sm = rsm;                                   // [8][K]
-  float *be_sm = th_sm + (size_t)kRankWarps * a.K;      // [chunk][K + 1]
-  unsigned long long *key_sm = reinterpret_cast<unsigned long long *>(be_sm + (size_t)a.chunk * (a.K + 1)); // [8][chunk]
+  extern __shared__ float rsm[]; // [kRankWarps][K]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ua = blockIdx.x * kRankWarps + w; // position in the user list
-  const bool live = ua < a.nu;
-  const uint32_t u = live ? a.users[ua] : 0u;
-  for (uint32_t k = lane; k < a.K; k += 32) th_sm[(size_t)w * a.K + k] = live ? a.Et[(size_t)u * a.ld + k] : 0.f;
-  const float ub = (live && a.Etb) ? a.Etb[u] : 0.f;
-  const uint32_t *ex = a.excl_sorted + (live ? a.excl_ptr[ua] : 0);
-  const uint32_t exlen = live ? (uint32_t)(a.excl_ptr[ua + 1] - a.excl_ptr[ua]) : 0u;
-  const uint64_t q0 = live ? a.q_ptr[ua] : 0, q1 = live ? a.q_ptr[ua + 1] : 0;
+  if (ua >= a.nu) return;
+  const uint32_t u = a.users[ua];
+  float *myth = rsm + (size_t)w * a.K;
+  for (uint32_t k = lane; k < a.K; k += 32) myth[k] = a.Et[(size_t)u * a.ld + k];
+  const float ub = a.Etb ? a.Etb[u] : 0.f;
+  const uint32_t *ex = a.excl_sorted + a.excl_ptr[ua];
+  const uint32_t exlen = (uint32_t)(a.excl_ptr[ua + 1] - a.excl_ptr[ua]);
   __syncwarp();
-  const float *myth = th_sm + (size_t)w * a.K;
-  // the queries' own keys, with the same routine from global rows
-  for (uint64_t q = q0 + lane; q < q1; q += 32) {
+  for (uint64_t q = a.q_ptr[ua] + lane; q < a.q_ptr[ua + 1]; q += 32) {
     const uint32_t it = a.q_idx[q];
     float s = rank_dot(myth, a.Eb + (size_t)it * a.ld, a.K);
     if (a.Etb) s += ub + a.Ebb[it];
@@ -598,32 +609,199 @@ __global__ void __launch_bounds__(kRankWarps * 32) rank_kernel(const RankArgs a)
     a.score_out[q] = __uint_as_float(bits);
     a.rank_out[q] = 0u;
   }
-  for (uint32_t i0 = 0; i0 < a.m; i0 += a.chunk) {
-    const uint32_t ni = min(a.chunk, a.m - i0);
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < ni * a.K; e += blockDim.x) {
-      const uint32_t r = e / a.K, k = e - r * a.K;
-      be_sm[(size_t)r * (a.K + 1) + k] = a.Eb[(size_t)(i0 + r) * a.ld + k];
+}
+
+__global__ void __launch_bounds__(kRankThreads, 1)
+rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const RankArgs a)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+  unsigned long long *qkey = reinterpret_cast<unsigned long long *>(gen_base + kStageBytes);         // [kQBatch][128]
+  uint32_t *hist = reinterpret_cast<uint32_t *>(gen_base + kStageBytes + kRankKeyBytes);             // [kQBatch + 1][128]
+  uint8_t *qorig = gen_base + kStageBytes + kRankKeyBytes + kRankHistBytes;                           // [kQBatch][128]
+  uint8_t *selfgt = qorig + kRankOrigBytes;                                                           // [kQBatch][128]
+  const uint32_t bar_off = kStageBytes + kRankKeyBytes + kRankHistBytes + 2 * kRankOrigBytes;
+  const uint32_t bar_full = base + bar_off, bar_empty = bar_full + 8, bar_tfull = bar_full + 16, bar_tempty = bar_full + 24;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen_base + bar_off + 32);
+  uint32_t *maxq_slot = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_m = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1); mbar_init(bar_empty, 1); mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 32 * kRankEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *maxq_slot = 0u;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // the passes this CTA needs: the largest query count among its rows, 32 at a time
+  if (threadIdx.x < kTileM) {
+    const uint32_t row = tile_m * kTileM + threadIdx.x;
+    if (row < a.nu) atomicMax(maxq_slot, (uint32_t)(a.q_ptr[row + 1] - a.q_ptr[row]));
+  }
+  __syncthreads();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t npass = (*maxq_slot + kQBatch - 1) / kQBatch;
+  const uint32_t total_tiles = npass * a.ntiles_n;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t jt = 0; jt < total_tiles; ++jt) {
+        const uint32_t j = jt % a.ntiles_n;
+        for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
+          mbar_wait_relaxed(bar_empty, (it & 1u) ^ 1u);
+          mbar_expect_tx(bar_full, kStageBytes);
+          tma_load_2d(base, &map_a_hi, bar_full, (int)(kb * kBlockK), (int)(tile_m * kTileM));
+          tma_load_2d(base + kABytes, &map_a_lo, bar_full, (int)(kb * kBlockK), (int)(tile_m * kTileM));
+          tma_load_2d(base + 2 * kABytes, &map_b_hi, bar_full, (int)(kb * kBlockK), (int)(j * kTileN));
+          tma_load_2d(base + 2 * kABytes + kBBytes, &map_b_lo, bar_full, (int)(kb * kBlockK), (int)(j * kTileN));
+        }
+      }
     }
-    __syncthreads();
-    if (!live) continue;
-    for (uint32_t r = lane; r < ni; r += 32) {
-      const uint32_t it = i0 + r;
-      float s = rank_dot(myth, be_sm + (size_t)r * (a.K + 1), a.K);
-      if (a.Etb) s += ub + a.Ebb[it];
-      uint32_t bits = __float_as_uint(s);
-      if ((int)bits < 0 || is_excluded(ex, exlen, it)) bits = 0u;
-      key_sm[(size_t)w * a.chunk + r] = ((unsigned long long)bits << 32) | (unsigned long long)(~it);
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t jt = 0; jt < total_tiles; ++jt) {
+        mbar_wait_relaxed(bar_tempty, (jt & 1u) ^ 1u);
+        tc_fence_after();
+        for (uint32_t kb = 0; kb < a.nkb; ++kb, ++it) {
+          mbar_wait_relaxed(bar_full, it & 1u);
+          tc_fence_after();
+          const uint64_t da_hi = make_desc_sw128(base), da_lo = make_desc_sw128(base + kABytes);
+          const uint64_t db_hi = make_desc_sw128(base + 2 * kABytes), db_lo = make_desc_sw128(base + 2 * kABytes + kBBytes);
+#pragma unroll
+          for (uint32_t kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 16 * 2) >> 4);
+            tc_mma_bf16(tmem_base, da_hi + adv, db_hi + adv, kIdesc, (kb | kk) != 0u);
+            tc_mma_bf16(tmem_base, da_hi + adv, db_lo + adv, kIdesc, 1u);
+            tc_mma_bf16(tmem_base, da_lo + adv, db_hi + adv, kIdesc, 1u);
+          }
+          tc_commit(bar_empty);
+        }
+        tc_commit(bar_tfull);
+      }
     }
-    __syncwarp();
-    const unsigned long long *mk = key_sm + (size_t)w * a.chunk;
-    for (uint64_t q = q0 + lane; q < q1; q += 32) {
-      const unsigned long long kq = a.q_key[q];
-      uint32_t cnt = 0;
-      for (uint32_t r = 0; r < ni; ++r) cnt += mk[r] > kq ? 1u : 0u;
-      a.rank_out[q] += cnt;
+  } else {
+    // ===== epilogue: two threads per user row, each half of every tile's columns =====
+    const int ew = warp - 2;                       // 0..7
+    const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                      // which half of the columns (warps 2-5: the quarter order is 2,3,0,1 twice)
+    const uint32_t r_in = (uint32_t)(q4 * 32 + lane);
+    const uint32_t row = tile_m * kTileM + r_in;
+    const bool live = row < a.nu;
+    const uint32_t *ex = nullptr;
+    uint32_t exlen = 0;
+    uint64_t q0 = 0, q1 = 0;
+    if (live) {
+      const uint64_t e0 = a.excl_ptr[row], e1 = a.excl_ptr[row + 1];
+      ex = a.excl_sorted + e0;
+      exlen = (uint32_t)(e1 - e0);
+      q0 = a.q_ptr[row]; q1 = a.q_ptr[row + 1];
     }
-    __syncwarp();
+    uint32_t jt = 0;
+    for (uint32_t pass = 0; pass < npass; ++pass) {
+      const uint64_t b0 = q0 + (uint64_t)pass * kQBatch;
+      const uint32_t nq = b0 < q1 ? (uint32_t)((q1 - b0) < (uint64_t)kQBatch ? (q1 - b0) : (uint64_t)kQBatch) : 0u;
+      if (half == 0) {
+        // this row's batch: keys ascending by insertion (<= 32 of them), unused slots = +inf; counts cleared
+        for (uint32_t j = 0; j < (uint32_t)kQBatch; ++j) {
+          unsigned long long k = j < nq ? a.q_key[b0 + j] : ~0ull;
+          uint32_t o = j;
+          // insert into the sorted prefix [0, j)
+          uint32_t p = j;
+          while (p > 0 && qkey[(p - 1) * kTileM + r_in] > k) {
+            qkey[p * kTileM + r_in] = qkey[(p - 1) * kTileM + r_in];
+            qorig[p * kTileM + r_in] = qorig[(p - 1) * kTileM + r_in];
+            --p;
+          }
+          qkey[p * kTileM + r_in] = k;
+          qorig[p * kTileM + r_in] = (uint8_t)o;
+          selfgt[j * kTileM + r_in] = 0;
+        }
+        for (uint32_t b = 0; b <= (uint32_t)kQBatch; ++b) hist[b * kTileM + r_in] = 0u;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kRankEpiWarps) : "memory");
+      uint32_t excur = 0;
+      for (uint32_t j = 0; j < a.ntiles_n; ++j, ++jt) {
+        const uint32_t col0 = j * kTileN + (uint32_t)half * (kTileN / 2);
+        const uint32_t lim = a.m > col0 ? a.m - col0 : 0u;
+        const uint32_t ncols = lim < (uint32_t)(kTileN / 2) ? lim : (uint32_t)(kTileN / 2);
+        uint32_t mask[kTileN / 64];
+#pragma unroll
+        for (int w = 0; w < kTileN / 64; ++w) mask[w] = 0u;
+        while (excur < exlen) { // the sorted exclusion list, restricted to this thread's columns of the tile
+          const uint32_t v = __ldg(ex + excur);
+          if (v >= col0 + (uint32_t)(kTileN / 2)) break;
+          if (v >= col0) {
+            const uint32_t o = v - col0, bit = 1u << (o & 31u);
+#pragma unroll
+            for (int w = 0; w < kTileN / 64; ++w) mask[w] |= ((o >> 5) == (uint32_t)w) ? bit : 0u;
+          }
+          ++excur;
+        }
+        mbar_wait(bar_tfull, jt & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (uint32_t c = 0; c < kTileN / 64; ++c) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * (kTileN / 2) + c * 32, r);
+          tc_wait_ld();
+          const uint32_t valid = ncols > c * 32 ? ncols - c * 32 : 0u;
+          const uint32_t mw = mask[c];
+          const uint32_t inv0 = ~(col0 + c * 32);
+          if (live && nq > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if ((uint32_t)i >= valid) continue; // only the last tile has columns past the last item
+              uint32_t bits = ((mw >> i) & 1u) ? 0u : r[i];
+              if ((int)bits < 0) bits = 0u;
+              const unsigned long long x = ((unsigned long long)bits << 32) | (unsigned long long)(inv0 - (uint32_t)i);
+              // b = number of batch keys smaller than x: 5-step search over the 32 sorted slots (pads are +inf)
+              uint32_t b = 0;
+#pragma unroll
+              for (uint32_t step = kQBatch / 2; step >= 1; step >>= 1)
+                if (qkey[(b + step - 1) * kTileM + r_in] < x) b += step;
+              if (b < (uint32_t)kQBatch && qkey[b * kTileM + r_in] < x) ++b; // 32 slots need a 6th comparison
+              atomicAdd(hist + b * kTileM + r_in, 1u); // the row's other thread counts into the same table
+              // the query item itself, with the tensor-core score: next to the insertion point.  It must not count
+              // towards its own rank, whichever of its two scores is larger.
+              const uint32_t xlo = (uint32_t)x;
+              if (b < (uint32_t)kQBatch && (uint32_t)qkey[b * kTileM + r_in] == xlo) { /* key_q >= x: not counted anyway */ }
+              else if (b > 0 && (uint32_t)qkey[(b - 1) * kTileM + r_in] == xlo) selfgt[(b - 1) * kTileM + r_in] = 1; // x > key_q
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kRankEpiWarps) : "memory");
+      if (half == 0 && live) {
+        // rank of sorted slot j = items counted in buckets above j, minus the query item itself if it landed there
+        uint32_t above = 0;
+        for (int j = kQBatch - 1; j >= 0; --j) {
+          above += hist[(j + 1) * kTileM + r_in];
+          if ((uint32_t)j < nq) a.rank_out[b0 + qorig[j * kTileM + r_in]] = above - (uint32_t)selfgt[j * kTileM + r_in];
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kRankEpiWarps) : "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 

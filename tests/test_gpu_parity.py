@@ -436,6 +436,8 @@ def test_item_ranks_match_full_sorted_list(flags, k):
     ei = np.concatenate(excl).astype(np.uint32)
     qs = [rng.choice(m, size=rng.integers(0, 25), replace=False).astype(np.uint32) for _ in users]
     qs[2] = np.concatenate([qs[2], excl[2][:3]]).astype(np.uint32)  # queries that are excluded items: rank among the zeros
+    qs[5] = rng.choice(m, size=70, replace=False).astype(np.uint32)   # more than one batch of 32: several counting passes
+    qs[140] = np.arange(m, dtype=np.uint32)                           # every item of one user: ranks are a permutation
     qp = np.zeros(len(users) + 1, np.uint64)
     qp[1:] = np.cumsum([len(x) for x in qs])
     qi = np.concatenate(qs).astype(np.uint32)
@@ -456,6 +458,10 @@ def test_item_ranks_match_full_sorted_list(flags, k):
             assert abs(int(ranks[q]) - want) < near, (a, it, ranks[q], want)
             exact += int(ranks[q]) == want
     assert exact >= 0.98 * len(qi)
+    full = ranks[int(qp[140]):int(qp[141])]
+    # all items queried: every position once -- up to pairs of scores closer than the fp32 / tensor-core rounding gap,
+    # where each of the two may see the other one ahead
+    assert int(full.max()) <= m - 1 and len(set(full.tolist())) >= m - 6
 
 
 def test_topn_rejects_bad_arguments():

@@ -1,0 +1,20 @@
+#!/bin/bash
+# ncu_export.sh REPORT.ncu-rep OUT_PREFIX : selected raw metrics per launch as CSV (small enough to travel back from the GPU box)
+rep=$1; out=$2
+ncu -i "$rep" --page raw --csv 2>/dev/null | python - "$out" <<'PY'
+import csv, sys
+rows = list(csv.reader(sys.stdin))
+if len(rows) < 3:
+    sys.exit(0)
+hdr = rows[0]
+pick = [i for i, h in enumerate(hdr) if h in ("ID", "Kernel Name", "Grid Size", "Block Size") or any(s in h for s in (
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct", "lts__throughput.avg.pct",
+    "l1tex__throughput.avg.pct", "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__lsu_writeback_active.avg.pct",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__issue_active.avg.pct", "sm__warps_active.avg.pct",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_tensor", "sm__pipe_tensor", "smsp__average_warps_issue_stalled_long_scoreboard_per", "smsp__average_warps_issue_stalled_short_scoreboard_per",
+    "smsp__average_warps_issue_stalled_wait_per", "smsp__average_warps_issue_stalled_barrier_per", "smsp__average_warps_issue_stalled_math_pipe", "smsp__average_warps_issue_stalled_lg_throttle",
+    "smsp__average_warps_issue_stalled_mio_throttle", "launch__registers_per_thread", "launch__occupancy_limit", "sm__throughput.avg.pct", "sm__pipe_fma_cycles_active.avg.pct", "sm__inst_executed_pipe_xu.avg.pct"))]
+w = csv.writer(open(sys.argv[1] + "_summary.csv", "w"))
+for r in rows:
+    w.writerow([r[i] if i < len(r) else "" for i in pick])
+PY
