@@ -9,10 +9,10 @@
 // Kp >= 32, the next power of two below that) -- the gather of one K=100 row
 // then costs 4 L1 wavefronts instead of 7:
 //   A      [R x ld]  exp(Elog - rowmax)      sweep input (gathered by the other side)
-//   Elog   [R x ld]  expected log            fallback path + hpf_get_state
-//   Ev     [R x ld]  expectation             rate sums, held-out ll, top-N
-//   shape  [R x ld]  Gamma shape             hpf_get_state / checkpoints
-//   rate   [R x ld] (hier) or [Kp]           hpf_get_state / checkpoints
+//   shape  [R x ld]  Gamma shape             written every iteration, with A and the two rate terms
+//   Elog   [R x ld]  expected log            materialised on demand (derive_kernel): hpf_get_state, ELBO, exact fallback
+//   Ev     [R x ld]  expectation             materialised on demand: held-out ll, top-N, item ranks
+//   rate   [R x ld] (hier) or [Kp]           materialised on demand: hpf_get_state / checkpoints
 //   T      [R x ld]  sweep output sum (y/Z) * A_other   (+ Tpart for split rows)
 //   Tdirect[R x ld]  exact-fallback accumulator (all zero in normal operation)
 // plus per-row vectors (shift, xi/eta GPArray, bias GPMatrix, aux) and the
@@ -135,6 +135,7 @@ struct WorkList {       // segments of one orientation: (chunk of rows, L2 tile,
   uint32_t *multi_row = nullptr, *multi_first = nullptr, *multi_cnt = nullptr;
   const uint32_t *idx = nullptr; // device, per nonzero
   const uint8_t *y = nullptr;
+  bool packed = false;           // idx carries the rating in its top byte (gathered side < 2^24 rows)
   size_t seg_cap = 0, seg_out_cap = 0, multi_cap[3] = { 0, 0, 0 };
   // chunks of rows, launched one after the other (all-reduce of chunk c under the sweep of chunk c + 1)
   uint32_t nchunks = 1, chunk_rows = 0;
@@ -173,6 +174,9 @@ struct hpf_ctx {
   bool hier = false, bias = false, binary = false, jacobi = false;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // hpf_set_ratings_csr: the ratings' upload runs under the first device sort
+  cudaEvent_t ev_col = nullptr, ev_y = nullptr;
+  bool y_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[16] = { nullptr };
   bool profiling = false;
@@ -196,6 +200,7 @@ struct hpf_ctx {
   bool l2_tile_forced = false;          // HPF_L2_TILE_KB (tests): ignore the run-length cap
   uint32_t *scratch_u32 = nullptr;
   uint32_t seg_len = 512;
+  bool pack_ok = true;           // HPF_PACK=0 (tests / A-B timing): keep index and rating in separate streams
   int sweep_g = 0, sweep_v = 0;
   bool aux_dirty = true, ratings_set = false, th_colsum_global = false;
   // item-side reduce block [T_beta | Tb_beta | colsum_theta | fallback flag]: T_beta is all-reduced chunk by
@@ -396,6 +401,14 @@ template <int G> int launch_sweep_g(hpf_ctx *c, const SweepArgs &a)
   return fail(c, HPF_EINVAL, "unsupported sweep shape G=%d V=%d", G, c->sweep_v);
 }
 
+ElogSrc elog_src(const hpf_ctx *c, const Side &s)
+{
+  ElogSrc e;
+  e.Elog = s.Elog; e.shape = s.shape; e.rate_row = s.rate_row; e.rate_col = s.rate_col;
+  e.valid = s.derived_valid ? 1 : 0; e.hier = c->hier ? 1 : 0;
+  return e;
+}
+
 // sweep over the segments of chunk `chunk` of the row side's work list (chunk < 0: all of them)
 int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside, int chunk = -1)
 {
@@ -404,12 +417,12 @@ int launch_sweep(hpf_ctx *c, Side &rowside, Side &colside, int chunk = -1)
   const WorkList &w = rowside.wl;
   const uint32_t s0 = chunk < 0 ? 0u : w.chunk_seg[chunk], s1 = chunk < 0 ? w.nsegs : w.chunk_seg[chunk + 1];
   a.seg = w.seg + s0; a.seg_out = w.seg_out + s0; a.nsegs = s1 - s0; a.R = rowside.R;
-  a.idx = w.idx; a.y = w.y;
+  a.idx = w.idx; a.y = w.y; a.packed = w.packed ? 1u : 0u;
   a.Arow = rowside.A; a.Acol = colside.A;
   a.T = rowside.T; a.Tpart = rowside.Tpart;
   a.row_aux = rowside.aux; a.col_aux = colside.aux;
   a.Tb = rowside.Tb; a.Tbpart = rowside.Tbpart;
-  a.ElogRow = rowside.Elog; a.ElogCol = colside.Elog;
+  a.ElogRow = elog_src(c, rowside); a.ElogCol = elog_src(c, colside);
   a.ElogbRow = rowside.b_Elog; a.ElogbCol = colside.b_Elog;
   a.Tdirect = rowside.Tdirect; a.Tbdirect = rowside.Tbdirect;
   a.direct_flag = rowside.direct_flag; a.slow_count = c->slow_count;
@@ -460,7 +473,7 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   a.R = s.R; a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4; a.ld4 = c->ld / 4;
   a.T = reinterpret_cast<const float4 *>(s.T); a.Tdirect = reinterpret_cast<float4 *>(s.Tdirect); a.direct_flag = s.direct_flag;
   a.direct_flag_all = (!theta && c->mg_exact && c->nranks > 1) ? c->red_flag : nullptr;
-  a.A = reinterpret_cast<float4 *>(s.A); a.Elog = reinterpret_cast<float4 *>(s.Elog); a.shape = reinterpret_cast<float4 *>(s.shape);
+  a.A = reinterpret_cast<float4 *>(s.A); a.shape = reinterpret_cast<float4 *>(s.shape);
   a.shift = s.shift;
   a.hier = c->hier; a.colsum_other = colsum_other;
   a.rate_vec = s.rate_col; a.rate_row = s.rate_row;
@@ -475,8 +488,6 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   if (theta && c->dense.on && !c->dense.a_dirty) { // keep the dense head's operand copy of A in step
     a.split_hi = c->dense.a_hi; a.split_lo = c->dense.a_lo; a.split_ld = head::kFact;
   }
-  // hier: the column term of the rate this update uses, kept for derive_kernel (the GR vector is written by the kernel)
-  if (c->hier) CU(cudaMemcpyAsync(s.rate_col, colsum_other, sizeof(float) * c->Kp, cudaMemcpyDeviceToDevice, c->stream));
   s.derived_valid = false;
   switch ((c->K4 + 31) / 32) {
   case 1: TRY(launch_update_v<1>(c, a, s.update_grid)); break;
@@ -490,7 +501,7 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   default: return fail(c, HPF_EINVAL, "unsupported factor count %u", c->K);
   }
   const bool mg = c->nranks > 1;
-  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(
+  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 32 * kFinalizeGroups, 0, c->stream>>>(
       s.colsum_partial, s.update_grid, c->Kp, s.colsum, s.direct_flag,
       theta && mg ? c->be.direct_flag : nullptr, theta && mg ? c->red_flag : nullptr,
       !theta && mg ? c->red_flag : nullptr, !theta && mg ? c->mg_fired : nullptr);
@@ -499,14 +510,15 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
   return 0;
 }
 
-// E[v] and the rate matrix of a side, materialised from shape and the rate terms of the last update
-// (report-window consumers: held-out ll, top-N, ELBO, hpf_get_state)
+// E[v], E[log v] and the rate matrix of a side, materialised from shape and the rate terms of the last update
+// (report-window consumers: held-out ll, top-N, ELBO, hpf_get_state; afterwards the exact fallback reads the array too)
 int ensure_derived(hpf_ctx *c, Side &s)
 {
   if (s.derived_valid) return 0;
   DeriveArgs a;
   a.R = s.R; a.K = c->K; a.K4 = c->K4; a.ld4 = c->ld / 4;
   a.shape = reinterpret_cast<const float4 *>(s.shape); a.Ev = reinterpret_cast<float4 *>(s.Ev);
+  a.Elog = reinterpret_cast<float4 *>(s.Elog);
   a.rate = c->hier ? reinterpret_cast<float4 *>(s.rate) : nullptr;
   a.hier = c->hier; a.rate_row = s.rate_row; a.rate_col = s.rate_col;
   const uint64_t total = (uint64_t)s.R * c->K4;
@@ -525,7 +537,7 @@ int refresh_colsum(hpf_ctx *c, Side &s)
   colsum_partial_kernel<<<s.update_grid, kUpdateWarps * 32, sm, c->stream>>>(s.Ev, s.R, c->Kp, c->ld, s.colsum_partial);
   c->launches++;
   CU(cudaGetLastError());
-  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 256, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
+  colsum_finalize_kernel<<<(c->Kp + 31) / 32, 32 * kFinalizeGroups, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
                                                                      nullptr, nullptr, nullptr, nullptr, nullptr);
   c->launches++;
   CU(cudaGetLastError());
@@ -601,6 +613,18 @@ struct Scratch {
   }
 };
 
+// One orientation of the ratings on the device: the nonzeros ordered by (tile of col, row), the
+// gathered-side index and the rating permuted accordingly, and the run pointers (run (t, r) at
+// d_run[t * R + r]).  d_row / d_col / d_y are per nonzero in the caller's order.  presorted: the input is
+// already ordered by row and d_rowptr is its row pointer -- with one tile that IS the orientation.
+struct Orientation {
+  uint32_t ntiles = 1, tile_cols = 0;
+  const uint64_t *d_run = nullptr; // device, ntiles * R + 1
+  const uint32_t *d_idx = nullptr;
+  const uint8_t *d_y = nullptr;
+  bool packed = false;             // d_idx = index | rating << 24, d_y unused
+};
+
 // ---- work lists, built on the device (kernels and the ordering: hpf_kernels.cuh, "work lists") -------------
 // Everything is enqueued on the ctx stream; the counts (segments, partial slots, multi-segment rows, chunk
 // boundaries) land in pinned memory and are read by finish_worklist after the caller's next synchronisation.
@@ -621,12 +645,11 @@ size_t worklist_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, uint32_t L,
 }
 
 int build_worklist_device(hpf_ctx *c, Arena &dev, Arena &pin, Side &s, const uint64_t *d_run, uint32_t ntiles, uint64_t nnz,
-                          const uint32_t *d_skip_slot, uint32_t nchunks, const uint32_t *d_idx, const uint8_t *d_y,
-                          size_t cub_bytes, WlPending *pend)
+                          const uint32_t *d_skip_slot, uint32_t nchunks, const Orientation &o, size_t cub_bytes, WlPending *pend)
 {
   const uint32_t R = s.R, L = c->seg_len;
   WorkList &w = s.wl;
-  w.idx = d_idx; w.y = d_y;
+  w.idx = o.d_idx; w.y = o.d_y; w.packed = o.packed;
   nchunks = std::max(1u, std::min(std::min(nchunks, kMaxChunks), R));
   const uint32_t chunk_rows = (R + nchunks - 1) / nchunks;
   nchunks = (R + chunk_rows - 1) / chunk_rows;
@@ -691,20 +714,19 @@ int finish_worklist(hpf_ctx *c, Side &s, const WlPending &p)
   return 0;
 }
 
-// One orientation of the ratings on the device: the nonzeros ordered by (tile of col, row), the
-// gathered-side index and the rating permuted accordingly, and the run pointers (run (t, r) at
-// d_run[t * R + r]).  d_row / d_col / d_y are per nonzero in the caller's order.  presorted: the input is
-// already ordered by row and d_rowptr is its row pointer -- with one tile that IS the orientation.
-struct Orientation {
-  uint32_t ntiles = 1, tile_cols = 0;
-  const uint64_t *d_run = nullptr; // device, ntiles * R + 1
-  const uint32_t *d_idx = nullptr;
-  const uint8_t *d_y = nullptr;
-};
-
 size_t orientation_dev_bytes(uint64_t nnz, uint32_t R, uint32_t ntiles, size_t cub_bytes)
 {
-  return 2 * pad256(nnz * 4) + 2 * pad256(nnz * 8) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
+  return 4 * pad256(nnz * 4) + pad256(((size_t)ntiles * R + 1) * 8) + pad256(cub_bytes) + 4096;
+}
+
+// the ratings travel host -> device on copy_stream, after the indices; the first kernel that reads them waits here
+int wait_for_ratings(hpf_ctx *c)
+{
+  if (c->y_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_y, 0));
+    c->y_pending = false;
+  }
+  return 0;
 }
 
 int orient_device(hpf_ctx *c, Arena &dev, uint64_t nnz, const uint32_t *d_row, const uint32_t *d_col, const uint8_t *d_y,
@@ -713,14 +735,22 @@ int orient_device(hpf_ctx *c, Arena &dev, uint64_t nnz, const uint32_t *d_row, c
 {
   o->ntiles = tiles_for(c, C, R, nnz);
   o->tile_cols = (uint32_t)(((uint64_t)C + o->ntiles - 1) / o->ntiles);
+  o->packed = C < (1u << 24) && c->pack_ok; // the sweep then reads ONE word per nonzero and broadcasts one value
   if (presorted && o->ntiles == 1) {
     o->d_run = d_rowptr; o->d_idx = d_col; o->d_y = d_y;
+    if (o->packed && nnz > 0) {
+      TRY(ensure(c, own_idx, own_idx_cap, nnz));
+      TRY(wait_for_ratings(c));
+      pack_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(d_col, d_y, nnz, *own_idx);
+      c->launches++;
+      o->d_idx = *own_idx; o->d_y = nullptr;
+    } else o->packed = false;
     return 0;
   }
   const size_t nruns = (size_t)o->ntiles * R;
   TRY(ensure(c, own_idx, own_idx_cap, nnz));
-  if (d_y) TRY(ensure(c, own_y, own_y_cap, nnz));
-  o->d_idx = *own_idx; o->d_y = d_y ? *own_y : nullptr;
+  if (d_y && !o->packed) TRY(ensure(c, own_y, own_y_cap, nnz));
+  o->d_idx = *own_idx; o->d_y = (d_y && !o->packed) ? *own_y : nullptr;
   uint64_t *d_run = dev.get<uint64_t>(nruns + 1);
   if (!d_run) return fail(c, HPF_ENOMEM, "device set-up arena too small");
   o->d_run = d_run;
@@ -728,18 +758,19 @@ int orient_device(hpf_ctx *c, Arena &dev, uint64_t nnz, const uint32_t *d_row, c
     CU(cudaMemsetAsync(d_run, 0, (nruns + 1) * 8, c->stream));
     return 0;
   }
-  uint32_t *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz);
-  uint64_t *val = dev.get<uint64_t>(nnz), *val2 = dev.get<uint64_t>(nnz);
+  uint32_t *key = dev.get<uint32_t>(nnz), *key2 = dev.get<uint32_t>(nnz), *pos = dev.get<uint32_t>(nnz), *pos2 = dev.get<uint32_t>(nnz);
   void *d_tmp = dev.get<char>(cub_bytes);
-  if (!key || !key2 || !val || !val2 || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
+  if (!key || !key2 || !pos || !pos2 || !d_tmp) return fail(c, HPF_ENOMEM, "device set-up arena too small");
   size_t tmp_bytes = cub_bytes;
   const unsigned nb = (unsigned)((nnz + 255) / 256);
-  // one stable sort by (tile of the gathered-side index, row); the payload carries that index and the rating
-  orient_key_kernel<<<nb, 256, 0, c->stream>>>(d_row, d_col, d_y, o->tile_cols, R, nnz, key, val);
-  CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint64_t *)val, val2, (int64_t)nnz, 0,
+  // one stable sort of the positions by (tile of the gathered-side index, row); the index and the rating follow through
+  // the sorted positions -- the ratings may still be on their way from the host until then
+  orient_key_kernel<<<nb, 256, 0, c->stream>>>(d_row, d_col, o->tile_cols, R, nnz, key, pos);
+  CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, (const uint32_t *)key, key2, (const uint32_t *)pos, pos2, (int64_t)nnz, 0,
                                      bits_for((uint64_t)nruns), c->stream));
-  orient_unpack_kernel<<<nb, 256, 0, c->stream>>>(val2, nnz, *own_idx, d_y ? *own_y : nullptr);
   run_ptr_kernel<<<(unsigned)((nnz + 256) / 256), 256, 0, c->stream>>>(key2, nnz, (uint32_t)nruns, d_run);
+  TRY(wait_for_ratings(c));
+  orient_gather_kernel<<<nb, 256, 0, c->stream>>>(pos2, d_col, d_y, nnz, *own_idx, o->d_y ? *own_y : nullptr, o->packed ? 1 : 0);
   c->launches += 3;
   CU(cudaGetLastError());
   return 0;
@@ -791,27 +822,31 @@ int launch_dense_head(hpf_ctx *c)
   const int head_threads = head::head_threads(c->head_variant & 7);
   CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head::kSmemBytes));
   const uint32_t grid = std::min<uint32_t>(d.ntiles, (uint32_t)c->sm_count);
+  const size_t part_stride = (size_t)grid * head::kHead * head::kFact;
+  // the operand rows of ALL head blocks in one launch (b_hi / b_lo and head_ids are contiguous over the blocks)
+  if (c->bias)
+    head::split_aux_kernel<<<64 * d.nblocks, 256, 0, c->stream>>>(c->be.A, c->ld, c->Kp, c->be.aux, 1, d.head_ids, d.nhead, d.nblocks * head::kHead, d.b_hi, d.b_lo);
+  else
+    topk::split_kernel<<<64 * d.nblocks, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, d.head_ids, d.nhead, d.nblocks * head::kHead, head::kFact, d.b_hi, d.b_lo);
+  c->launches++;
   for (uint32_t b = 0; b < d.nblocks; ++b) { // one pass over the users per block of 128 head items
-    const uint32_t nh = std::min<uint32_t>(head::kHead, d.nhead - b * head::kHead);
-    const size_t boff = (size_t)b * head::kHead * head::kFact;
     const uint32_t *ids = d.head_ids + (size_t)b * head::kHead;
-    float *part = d.dB_part + (size_t)b * grid * head::kHead * head::kFact;
-    if (c->bias)
-      head::split_aux_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->Kp, c->be.aux, 1, ids, nh, head::kHead, d.b_hi + boff, d.b_lo + boff);
-    else
-      topk::split_kernel<<<64, 256, 0, c->stream>>>(c->be.A, c->ld, c->K, nullptr, 0, ids, nh, head::kHead, head::kFact, d.b_hi + boff, d.b_lo + boff);
+    float *part = d.dB_part + (size_t)b * part_stride;
     head::HeadArgs a;
-    a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld;
+    a.n = n; a.ntiles = d.ntiles; a.K = c->Kp; a.ld = c->ld; a.Ktrue = c->K;
     a.Y = reinterpret_cast<const uint8_t *>(d.Yw) + (size_t)b * n_pad * head::kHead; a.head_ids = ids;
     a.T_theta = c->th.T; a.dB_part = part;
-    a.ElogT = c->th.Elog; a.ElogB = c->be.Elog; a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
+    a.ElogT = elog_src(c, c->th); a.ElogB = elog_src(c, c->be); a.TdirectT = c->th.Tdirect; a.TdirectB = c->be.Tdirect;
     a.flagT = c->th.direct_flag; a.flagB = c->be.direct_flag; a.slow_count = c->slow_count;
     a.Tb_theta = c->bias ? c->th.Tb : nullptr;
     a.ElogbT = c->th.b_Elog; a.ElogbB = c->be.b_Elog; a.TbdirectT = c->th.Tbdirect; a.TbdirectB = c->be.Tbdirect;
     kernel<<<grid, head_threads, head::kSmemBytes, c->stream>>>(d.map_a_hi, d.map_a_lo, d.map_b_hi[b], d.map_b_lo[b], a);
-    head::head_reduce_kernel<<<nh, 128, 0, c->stream>>>(part, grid, ids, c->Kp, c->ld, c->be.T, c->bias ? c->be.Tb : nullptr);
-    c->launches += 3;
+    c->launches++;
   }
+  // the head items' T_beta rows from the CTAs' partial sums, all blocks in one launch (unused slots return at once)
+  head::head_reduce_kernel<<<d.nblocks * head::kHead, head::kFact * head::kReduceSplit, 0, c->stream>>>(
+      d.dB_part, part_stride, grid, d.head_ids, c->Kp, c->ld, c->be.T, c->bias ? c->be.Tb : nullptr);
+  c->launches++;
   CU(cudaGetLastError());
   return 0;
 }
@@ -1040,6 +1075,7 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (const char *e = getenv("HPF_DENSE_HEAD")) n->dense_head_mode = atoi(e);
   if (const char *e = getenv("HPF_DENSE_BLOCK_SHARE")) n->dense_block_share = atof(e);
   if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 7;
+  if (const char *e = getenv("HPF_PACK")) n->pack_ok = atoi(e) != 0;
   if (const char *e = getenv("HPF_AR_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= (int)kMaxChunks) n->ar_chunks = v; }
   if (const char *e = getenv("HPF_MG_EXACT")) n->mg_exact = atoi(e) != 0; // tests: fallback buffers inside the all-reduce from the start
   c = n;
@@ -1047,6 +1083,8 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   do {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, HPF_ECUDA, "cudaStreamCreate failed"); break; }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, HPF_ECUDA, "cudaStreamCreate failed"); break; }
+    cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_y, cudaEventDisableTiming);
     for (auto &e : c->pev) cudaEventCreate(&e);
     c->th.prior_shape = cfg->theta_shape; c->th.prior_rate = cfg->theta_rate;
     c->th.pr_prior_shape = cfg->thetarate_shape; c->th.pr_prior_rate = cfg->thetarate_rate;
@@ -1106,6 +1144,9 @@ void hpf_destroy(hpf_ctx *c)
   }
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_col) cudaEventDestroy(c->ev_col);
+  if (c->ev_y) cudaEventDestroy(c->ev_y);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
@@ -1138,6 +1179,8 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   c->ratings_set = false;
   c->nnz = nnz;
   c->pin_arena.pinned_host = true;
+  CU(cudaStreamSynchronize(c->copy_stream)); // a copy left over from a call that failed half-way
+  c->y_pending = false;
   const uint32_t L = c->seg_len;
   const uint32_t th_t = tiles_for(c, m, n, nnz), be_t = tiles_for(c, n, m, nnz);
   const bool try_dense = c->dense_head_mode != 0 && c->Kp + (c->bias ? 2u : 0u) <= (uint32_t)head::kFact && nnz > 0;
@@ -1181,9 +1224,15 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (nnz > 0) {
     CU(cudaMemcpyAsync(c->csr_idx, col_idx, nnz * 4, cudaMemcpyHostToDevice, c->stream));
-    if (y) CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->stream));
+    if (y) { // the ratings follow the indices on the copy stream: nothing needs them before the first sort is done
+      CU(cudaEventRecord(c->ev_col, c->stream));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->ev_col, 0));
+      CU(cudaMemcpyAsync(c->csr_y, y, nnz, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaEventRecord(c->ev_y, c->copy_stream));
+      c->y_pending = true;
+    }
     check_range_kernel<<<nb, 256, 0, c->stream>>>(c->csr_idx, nnz, m, c->scratch_u32); // every item index must be < n_items
-    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
+    expand_rows_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(d_rowptr, n, nnz, d_rowof);
     c->launches += 2;
   }
   if (c->logl) { // hpf_elbo walks the ratings user by user
@@ -1260,7 +1309,7 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     c->launches++;
   }
   // the item pass has no rows for head items: head_kernel produces their T_beta rows
-  TRY(build_worklist_device(c, dev, pin, c->be, io.d_run, io.ntiles, nnz, d_slot, item_chunks, io.d_idx, io.d_y, cub_bytes, &ip));
+  TRY(build_worklist_device(c, dev, pin, c->be, io.d_run, io.ntiles, nnz, d_slot, item_chunks, io, cub_bytes, &ip));
   if (dense_head) {
     const uint64_t ntail = nnz - head_nnz;
     TRY(ensure(c, &c->tail_idx, &c->tail_idx_cap, nnz));
@@ -1307,16 +1356,16 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
     if (tiles_for(c, m, n, ntail) > 1 && ntail > 0) {
       d_tailrow = dev.get<uint32_t>(ntail);
       if (!d_tailrow) return fail(c, HPF_ENOMEM, "set-up arena too small (tail rows)");
-      expand_rows_kernel<<<(unsigned)((ntail + 255) / 256), 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
+      expand_rows_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(d_tailptr, n, ntail, d_tailrow);
       c->launches++;
     }
     TRY(orient_device(c, dev, ntail, d_tailrow, c->tail_idx, y ? c->tail_y : nullptr, true, d_tailptr, n, m, &c->upass_idx,
                       &c->upass_idx_cap, &c->upass_y, &c->upass_y_cap, cub_bytes, &uo));
-    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, ntail, nullptr, 1, uo.d_idx, uo.d_y, cub_bytes, &up));
+    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, ntail, nullptr, 1, uo, cub_bytes, &up));
   } else { // user pass = the CSR itself (L2-tiled when the item rows outgrow the budget)
     TRY(orient_device(c, dev, nnz, d_rowof, c->csr_idx, d_y, true, d_rowptr, n, m, &c->upass_idx, &c->upass_idx_cap, &c->upass_y,
                       &c->upass_y_cap, cub_bytes, &uo));
-    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, nnz, nullptr, 1, uo.d_idx, uo.d_y, cub_bytes, &up));
+    TRY(build_worklist_device(c, dev, pin, c->th, uo.d_run, uo.ntiles, nnz, nullptr, 1, uo, cub_bytes, &up));
   }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -1444,7 +1493,7 @@ int hpf_get_state(hpf_ctx *c, int which, double *shape, double *rate, double *Ev
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   };
   int rc = 0;
-  if ((which == HPF_THETA || which == HPF_BETA) && (rate || Ev)) {
+  if ((which == HPF_THETA || which == HPF_BETA) && (rate || Ev || Elogv)) {
     rc = ensure_derived(c, s);
     if (rc) { cudaFree(stage); return rc; }
   }
@@ -1774,7 +1823,7 @@ int hpf_topn(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_t *exc
     const unsigned nb = (unsigned)((nex + 255) / 256);
     CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
     check_range_kernel<<<nb, 256, 0, c->stream>>>(d_exidx, nex, m, c->scratch_u32);
-    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
+    expand_rows_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
     topk::excl_key_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, d_exidx, nex, d_key);
     c->launches += 3;
     uint32_t bad = 0;
@@ -1873,7 +1922,7 @@ int hpf_item_ranks(hpf_ctx *c, const uint32_t *users, uint32_t nu, const uint64_
     const unsigned nb = (unsigned)((nex + 255) / 256);
     CU(cudaMemsetAsync(c->scratch_u32, 0, 4, c->stream));
     check_range_kernel<<<nb, 256, 0, c->stream>>>(d_exidx, nex, m, c->scratch_u32);
-    expand_rows_kernel<<<nb, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
+    expand_rows_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(d_exptr, nu, nex, d_rowof);
     topk::excl_key_kernel<<<nb, 256, 0, c->stream>>>(d_rowof, d_exidx, nex, d_key);
     uint32_t bad = 0;
     CU(cudaMemcpyAsync(&bad, c->scratch_u32, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -69,7 +69,8 @@ constexpr uint32_t kIdescMM = kIdescBase | (1u << 15) | (1u << 16);// MMA 3: A M
 struct HeadArgs {
   uint32_t n;            // users (rows >= n of the padded operand arrays are zero)
   uint32_t ntiles;       // user tiles of 128
-  uint32_t K, ld;        // factors, row stride of T in floats
+  uint32_t K, ld;        // factors rounded up to 4, row stride of T in floats
+  uint32_t Ktrue;        // factors
   const uint8_t *Y;      // [ntiles * 128 x 128] ratings of the head block (0: none)
   const uint32_t *head_ids; // [128] item row of each head slot (0xffffffff: unused slot)
   float *T_theta;        // [n x ld]  += O        (rows owned by this tile: plain read-modify-write)
@@ -80,7 +81,7 @@ struct HeadArgs {
   const float *ElogbT, *ElogbB;
   float *TbdirectT, *TbdirectB;
   // exact fallback for a pair whose Z left the fp32 range
-  const float *ElogT, *ElogB;
+  ElogSrc ElogT, ElogB;
   float *TdirectT, *TdirectB;
   uint32_t *flagT, *flagB;
   unsigned long long *slow_count;
@@ -89,18 +90,32 @@ struct HeadArgs {
 // exact log-domain phi for one (user, item) pair, added to BOTH sides' fallback buffers (one thread)
 __device__ __noinline__ void slow_pair(const HeadArgs &a, uint32_t u, uint32_t it, float yv)
 {
-  const float *et = a.ElogT + (size_t)u * a.ld, *eb = a.ElogB + (size_t)it * a.ld;
   const bool bias = a.Tb_theta != nullptr;
   const float xbu = bias ? a.ElogbT[u] : -CUDART_INF_F, xbi = bias ? a.ElogbB[it] : -CUDART_INF_F;
+  // x_k = Elog theta_uk + Elog beta_ik, four at a time (a.K is a multiple of 4; pad columns give -inf); E[log v] is
+  // recomputed from shape and rate when the arrays are not current (load_elog4)
+  auto x4 = [&](uint32_t q) {
+    const float4 t4 = load_elog4(a.ElogT, u, q, a.ld / 4, a.Ktrue), b4 = load_elog4(a.ElogB, it, q, a.ld / 4, a.Ktrue);
+    return make_float4(t4.x + b4.x, t4.y + b4.y, t4.z + b4.z, t4.w + b4.w);
+  };
   float mx = fmaxf(xbu, xbi);
-  for (uint32_t k = 0; k < a.K; ++k) mx = fmaxf(mx, et[k] + eb[k]); // pad columns hold -inf
+  for (uint32_t q = 0; q < a.K / 4; ++q) {
+    const float4 x = x4(q);
+    mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+  }
   float sum = bias ? expf(xbu - mx) + expf(xbi - mx) : 0.f;
-  for (uint32_t k = 0; k < a.K; ++k) sum += expf(et[k] + eb[k] - mx);
+  for (uint32_t q = 0; q < a.K / 4; ++q) {
+    const float4 x = x4(q);
+    sum += expf(x.x - mx) + expf(x.y - mx) + expf(x.z - mx) + expf(x.w - mx);
+  }
   const float sc = yv / sum;
-  for (uint32_t k = 0; k < a.K; ++k) {
-    const float v = sc * expf(et[k] + eb[k] - mx);
-    atomicAdd(a.TdirectT + (size_t)u * a.ld + k, v);
-    atomicAdd(a.TdirectB + (size_t)it * a.ld + k, v);
+  for (uint32_t q = 0; q < a.K / 4; ++q) {
+    const float4 x = x4(q);
+    const float v[4] = { sc * expf(x.x - mx), sc * expf(x.y - mx), sc * expf(x.z - mx), sc * expf(x.w - mx) };
+    for (uint32_t j = 0; j < 4; ++j) {
+      atomicAdd(a.TdirectT + (size_t)u * a.ld + q * 4 + j, v[j]);
+      atomicAdd(a.TdirectB + (size_t)it * a.ld + q * 4 + j, v[j]);
+    }
   }
   if (bias) {
     atomicAdd(a.TbdirectT + u, sc * expf(xbu - mx));
@@ -391,22 +406,32 @@ __global__ void __launch_bounds__(256) split_aux_kernel(const float *A, uint32_t
   }
 }
 
-// T_beta[head item] = sum over CTAs of their dB partials, in CTA order (deterministic); pad columns 0
-__global__ void head_reduce_kernel(const float *dB_part, uint32_t nparts, const uint32_t *head_ids, uint32_t Kp, uint32_t ld, float *T,
-                                   float *Tb)
+// T_beta[head item] = sum over CTAs of their dB partials, in a fixed order (deterministic); pad columns 0.  One launch
+// for all head blocks: CTA x serves slot x % 128 of block x / 128 (that block's partials start block_stride floats
+// further on); thread (k, g) adds the partials p = g, g + 4, ... of column k, the four sub-sums are added in order.
+constexpr int kReduceSplit = 4;
+__global__ void __launch_bounds__(kFact * kReduceSplit)
+head_reduce_kernel(const float *dB_part, size_t block_stride, uint32_t nparts, const uint32_t *head_ids, uint32_t Kp, uint32_t ld,
+                   float *T, float *Tb)
 {
+  __shared__ float sub[kReduceSplit][kFact];
+  const uint32_t slot = blockIdx.x % kHead;
   const uint32_t it = head_ids[blockIdx.x];
   if (it == 0xffffffffu) return;
-  if (Tb != nullptr && threadIdx.x == 0) { // -bias: column Kp + 1 of dB is the item-bias sum
-    float s = 0.f;
-    for (uint32_t p = 0; p < nparts; ++p) s += dB_part[((size_t)p * kHead + blockIdx.x) * kFact + Kp + 1];
-    Tb[it] = s;
-  }
-  for (uint32_t k = threadIdx.x; k < ld; k += blockDim.x) {
-    float s = 0.f;
-    if (k < Kp)
-      for (uint32_t p = 0; p < nparts; ++p) s += dB_part[((size_t)p * kHead + blockIdx.x) * kFact + k];
-    T[(size_t)it * ld + k] = s;
+  const float *part = dB_part + (size_t)(blockIdx.x / kHead) * block_stride;
+  const uint32_t k = threadIdx.x % kFact, g = threadIdx.x / kFact;
+  float s = 0.f;
+  // columns < Kp hold the factor sums; with -bias column Kp + 1 is the item-bias sum
+  if (k < Kp || (Tb != nullptr && k == Kp + 1))
+    for (uint32_t p = g; p < nparts; p += kReduceSplit) s += part[((size_t)p * kHead + slot) * kFact + k];
+  sub[g][k] = s;
+  __syncthreads();
+  if (g == 0) {
+    float t = sub[0][k];
+#pragma unroll
+    for (int q = 1; q < kReduceSplit; ++q) t += sub[q][k];
+    if (k < ld) T[(size_t)it * ld + k] = k < Kp ? t : 0.f;
+    if (Tb != nullptr && k == Kp + 1) Tb[it] = t;
   }
 }
 

@@ -87,6 +87,8 @@ template <int V> __device__ __forceinline__ void axpy_rows(float sc, const float
   }
 }
 
+__device__ __forceinline__ float floor30(float v) { return v > 0.f ? v : 1e-30f; } // make_nonzero, gpbase.hh:27-44
+
 // digamma for x > 0 in fp32: upward recurrence to x >= 6, then the Stirling
 // series.  Replaces gsl_sf_psi at gpbase.hh:260,593,923.
 __device__ __forceinline__ float digammaf(float x)
@@ -119,13 +121,41 @@ __device__ __forceinline__ float digammaf(float x)
 // 128-bit loads, forms Z with a G-lane xor-shuffle reduction and accumulates
 // (y/Z) * B.  Replaces hgaprec.cc:1340-1366 / 928-942 / 1227-1248.
 // ---------------------------------------------------------------------------
+// E[log v] of a parameter matrix as the exact fallback needs it.  The dense update does not store it per iteration
+// (nothing on the fast path reads it): while `valid` is 0 it is recomputed from the stored shape and the two rate terms
+// with the operations update_kernel / derive_kernel use, so the value is bit for bit what they would have stored.
+// After hpf_set_state (expectations given by the caller, not functions of shape and rate) and after derive_kernel
+// the array itself is valid.
+struct ElogSrc {
+  const float *Elog, *shape;  // [. x ld]
+  const float *rate_row;      // [R]  (hier)
+  const float *rate_col;      // [Kp] (hier: column term; GR: the rate vector)
+  int valid, hier;
+};
+__device__ __forceinline__ float4 load_elog4(const ElogSrc &e, uint32_t row, uint32_t q, uint32_t ld4, uint32_t K)
+{
+  if (e.valid) return reinterpret_cast<const float4 *>(e.Elog)[(size_t)row * ld4 + q];
+  const float4 sh = reinterpret_cast<const float4 *>(e.shape)[(size_t)row * ld4 + q];
+  const float4 ct = reinterpret_cast<const float4 *>(e.rate_col)[q];
+  const float rr = e.hier ? e.rate_row[row] : 0.f;
+  float4 out;
+  const float *s = reinterpret_cast<const float *>(&sh), *c = reinterpret_cast<const float *>(&ct);
+  float *o = reinterpret_cast<float *>(&out);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    o[j] = q * 4 + j < K ? digammaf(floor30(s[j])) - logf(floor30(e.hier ? rr + c[j] : c[j])) : -CUDART_INF_F;
+  return out;
+}
+
 struct SweepArgs {
   const uint4 *seg;        // {begin_lo, begin_hi, row, len}
   const uint32_t *seg_out; // < R: row of T;  >= R: slot (out - R) of Tpart
   uint32_t nsegs;
   uint32_t R;              // rows on the row side
-  const uint32_t *idx;     // per nonzero: row number on the column side
-  const uint8_t *y;        // per nonzero rating, or nullptr (all ones)
+  const uint32_t *idx;     // per nonzero: row number on the column side; with `packed` the rating sits in its top byte
+  const uint8_t *y;        // per nonzero rating, or nullptr (all ones; unused with `packed`)
+  uint32_t packed;         // the column side has < 2^24 rows: one word (index | rating << 24) per nonzero, and one
+                           // shuffle fewer per nonzero in a loop that is bound by the L1 data pipe
   const float *Arow;       // [R x ld]  exp(Elog - shift), row side
   const float *Acol;       // [C x ld]  same, column side
   float *T;                // [R x ld]  out: sum (y/Z) * Acol
@@ -136,7 +166,7 @@ struct SweepArgs {
   float *Tb;               // [R] out: sum (y/Z) * col_aux.y
   float *Tbpart;           // [P]
   // exact fallback
-  const float *ElogRow, *ElogCol;   // [. x ld], padding = -inf
+  ElogSrc ElogRow, ElogCol;         // E[log v] of both sides (padding = -inf)
   const float *ElogbRow, *ElogbCol; // bias logs (or nullptr)
   float *Tdirect;          // [R x ld] += y*phi
   float *Tbdirect;         // [R]
@@ -156,28 +186,23 @@ __device__ __forceinline__ uint32_t group_mask(int lane)
 // Exact log-domain phi for one nonzero (called when Z left the fp32 range):
 // phi_k = exp(x_k - max) / sum, x_k = ElogRow_k + ElogCol_k (+ the two bias
 // logs), i.e. what get_phi + lognormalize compute; y*phi is added to Tdirect.
-struct SlowArgs { // by value: taking the address of kernel parameters would force a local copy
-  const float *ElogRow, *ElogCol, *ElogbRow, *ElogbCol;
-  float *Tdirect, *Tbdirect;
-  uint32_t *direct_flag;
-  unsigned long long *slow_count;
-  uint32_t K, K4, ld, ld4;
-};
-
+// Takes the kernel's own parameter block by reference (a __grid_constant__ parameter may have its address taken
+// without a local copy), so the rare call costs the hot loop no registers.
 template <int G, int V, bool BIAS>
-__device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uint32_t c, float yv, int lane)
+__device__ __noinline__ void sweep_slow_path(const SweepArgs &a, uint32_t row, uint32_t c, float yv, int lane)
 {
   const int gl = lane & (G - 1);
   const uint32_t mask = group_mask<G>(lane);
-  const float4 *er = reinterpret_cast<const float4 *>(a.ElogRow) + (size_t)row * a.ld4;
-  const float4 *ec = reinterpret_cast<const float4 *>(a.ElogCol) + (size_t)c * a.ld4;
+  float4 xs[V]; // x_k = Elog_row_k + Elog_col_k of this lane's float4 slots
   float mx = -CUDART_INF_F;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const uint32_t q = gl + v * G;
+    xs[v] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     if (q < a.K4) {
-      const float4 r4 = er[q], c4 = ec[q];
-      mx = fmaxf(mx, fmaxf(fmaxf(r4.x + c4.x, r4.y + c4.y), fmaxf(r4.z + c4.z, r4.w + c4.w)));
+      const float4 r4 = load_elog4(a.ElogRow, row, q, a.ld4, a.K), c4 = load_elog4(a.ElogCol, c, q, a.ld4, a.K);
+      xs[v] = make_float4(r4.x + c4.x, r4.y + c4.y, r4.z + c4.z, r4.w + c4.w);
+      mx = fmaxf(mx, fmaxf(fmaxf(xs[v].x, xs[v].y), fmaxf(xs[v].z, xs[v].w)));
     }
   }
   float xbr = -CUDART_INF_F, xbc = -CUDART_INF_F;
@@ -192,10 +217,7 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const uint32_t q = gl + v * G;
-    if (q < a.K4) {
-      const float4 r4 = er[q], c4 = ec[q];
-      sum += expf(r4.x + c4.x - mx) + expf(r4.y + c4.y - mx) + expf(r4.z + c4.z - mx) + expf(r4.w + c4.w - mx);
-    }
+    if (q < a.K4) sum += expf(xs[v].x - mx) + expf(xs[v].y - mx) + expf(xs[v].z - mx) + expf(xs[v].w - mx);
   }
   if (BIAS && gl == 0) sum += expf(xbr - mx) + expf(xbc - mx);
 #pragma unroll
@@ -206,12 +228,11 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
   for (int v = 0; v < V; ++v) {
     const uint32_t q = gl + v * G;
     if (q < a.K4) {
-      const float4 r4 = er[q], c4 = ec[q];
       const uint32_t k0 = q * 4;
-      if (k0 + 0 < a.K) atomicAdd(td + k0 + 0, sc * expf(r4.x + c4.x - mx));
-      if (k0 + 1 < a.K) atomicAdd(td + k0 + 1, sc * expf(r4.y + c4.y - mx));
-      if (k0 + 2 < a.K) atomicAdd(td + k0 + 2, sc * expf(r4.z + c4.z - mx));
-      if (k0 + 3 < a.K) atomicAdd(td + k0 + 3, sc * expf(r4.w + c4.w - mx));
+      if (k0 + 0 < a.K) atomicAdd(td + k0 + 0, sc * expf(xs[v].x - mx));
+      if (k0 + 1 < a.K) atomicAdd(td + k0 + 1, sc * expf(xs[v].y - mx));
+      if (k0 + 2 < a.K) atomicAdd(td + k0 + 2, sc * expf(xs[v].z - mx));
+      if (k0 + 3 < a.K) atomicAdd(td + k0 + 3, sc * expf(xs[v].w - mx));
     }
   }
   if (gl == 0) {
@@ -221,8 +242,57 @@ __device__ __noinline__ void sweep_slow_path(const SlowArgs a, uint32_t row, uin
   }
 }
 
+// Second walk over the warp's segments for the nonzeros whose Z left the fp32 range.  The hot loop only COUNTS them
+// (a call inside it costs registers and local-memory traffic in a kernel that is bound by the L1 data pipe); when a
+// warp has seen any, it comes here once: same chunks, same arithmetic for Z (so the same nonzeros are found), and
+// the exact log-domain path for each of them.  Called by all 32 lanes.
 template <int G, int V, bool BIAS>
-__global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kernel(const SweepArgs a)
+__device__ __noinline__ void sweep_redo_slow(const SweepArgs &a, uint32_t row, uint64_t begin, uint32_t len, uint32_t maxlen, bool have, int lane)
+{
+  const int gl = lane & (G - 1);
+  float4 ar[V];
+  const float4 *rp = reinterpret_cast<const float4 *>(a.Arow) + (size_t)row * a.ld4;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint32_t q = gl + v * G;
+    ar[v] = (have && len > 0u && q < a.K4) ? ldg4(rp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float2 raux = make_float2(0.f, 0.f);
+  if (BIAS && have) raux = __ldg(a.row_aux + row);
+  const uint32_t *ip = a.idx + begin;
+  const uint8_t *yp = a.y ? a.y + begin : nullptr;
+  const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
+  const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
+  for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
+    const uint32_t jj = j0 + gl;
+    const uint32_t cword = (jj < len) ? ip[jj] : 0u;
+    const uint32_t cbuf = a.packed ? (cword & 0x00ffffffu) : cword;
+    const float ybuf = (jj < len) ? (a.packed ? (float)(cword >> 24) : (yp != nullptr ? (float)yp[jj] : 1.f)) : 0.f;
+    const int tmax = (int)min((uint32_t)G, maxlen - j0);
+    for (int t = 0; t < tmax; ++t) {
+      const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
+      const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
+      float4 b[V];
+      const float4 *cp = acol + (size_t)c * a.ld4;
+#pragma unroll
+      for (int v = 0; v < V - 1; ++v) b[v] = ldg4(cp + gl + v * G);
+      b[V - 1] = ldg4(cp + q_last);
+      float dot = dot_rows<V>(ar, b);
+#pragma unroll
+      for (int off = G / 2; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      float z = dot;
+      if (BIAS) {
+        const float2 caux = __ldg(a.col_aux + c);
+        z += raux.x * caux.y + caux.x * raux.y;
+      }
+      const bool ok = z > kZMin && z < kZMax;
+      if (!ok && yv != 0.f) sweep_slow_path<G, V, BIAS>(a, row, c, yv, lane);
+    }
+  }
+}
+
+template <int G, int V, bool BIAS>
+__global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kernel(const __grid_constant__ SweepArgs a)
 {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (G - 1);
@@ -257,6 +327,8 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
   const uint32_t *ip = a.idx + begin;
   const uint8_t *yp = a.y ? a.y + begin : nullptr;
   const float4 *acol = reinterpret_cast<const float4 *>(a.Acol);
+  const bool packed = a.packed != 0u;
+  uint32_t nslow = 0;
   // Lanes past the last float4 of a row re-read that float4 (their row-side value is 0 and their sums are
   // never stored), so the loop carries no predicates.  Only the last of the V slots can be out of range.
   const uint32_t q_last = min((uint32_t)(gl + (V - 1) * G), a.K4 - 1u);
@@ -268,16 +340,24 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
   // (measured 10-65 % slower: profiles/r02d_sweep_pipeline_experiment.txt)
   for (uint32_t j0 = 0; j0 < maxlen; j0 += G) {
     const uint32_t jj = j0 + gl;
-    const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row
-    const float ybuf = (jj < len) ? (yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f) : 0.f; // 0: no contribution
+    const uint32_t cbuf = (jj < len) ? ld_stream_u32(ip + jj) : 0u; // 0 past the end: a valid row (and rating 0 when packed)
+    float ybuf = 0.f;                                                // 0: no contribution
+    if (!packed && jj < len) ybuf = yp != nullptr ? (float)ld_stream_u8(yp + jj) : 1.f;
     // the last chunk of the warp's longest segment may be short: walk only what exists (warp-uniform bound).  With
     // users sharded over GPUs most item rows hold a handful of local nonzeros, and a full chunk would gather row 0
     // for every missing one.
     const int tmax = (int)min((uint32_t)G, maxlen - j0);
     HPF_UNROLL(HPF_UNROLL_T)
     for (int t = 0; t < tmax; ++t) {
-      const uint32_t c = __shfl_sync(0xffffffffu, cbuf, t, G);
-      const float yv = __shfl_sync(0xffffffffu, ybuf, t, G);
+      const uint32_t cw = __shfl_sync(0xffffffffu, cbuf, t, G);
+      uint32_t c = cw;
+      float yv;
+      if (packed) { // warp-uniform
+        c = cw & 0x00ffffffu;
+        yv = (float)(cw >> 24);
+      } else {
+        yv = __shfl_sync(0xffffffffu, ybuf, t, G);
+      }
       float4 b[V];
       const float4 *cp = acol + (size_t)c * a.ld4;
 #pragma unroll
@@ -296,15 +376,11 @@ __global__ void __launch_bounds__(kSweepThreads, HPF_SWEEP_MINBLOCKS) sweep_kern
       const float sc = ok ? yv * frcp(z) : 0.f;
       axpy_rows<V>(sc, b, acc);
       if (BIAS) accb = fmaf(sc, caux.y, accb);
-      if (!ok && yv != 0.f) { // Z left the fp32 range: exact log-domain path (rare)
-        SlowArgs sa;
-        sa.ElogRow = a.ElogRow; sa.ElogCol = a.ElogCol; sa.ElogbRow = a.ElogbRow; sa.ElogbCol = a.ElogbCol;
-        sa.Tdirect = a.Tdirect; sa.Tbdirect = a.Tbdirect; sa.direct_flag = a.direct_flag;
-        sa.slow_count = a.slow_count; sa.K = a.K; sa.K4 = a.K4; sa.ld = a.ld; sa.ld4 = a.ld4;
-        sweep_slow_path<G, V, BIAS>(sa, row, c, yv, lane);
-      }
+      nslow += (!ok && yv != 0.f) ? 1u : 0u; // Z left the fp32 range: contributes nothing here, redone exactly below
     }
   }
+
+  if (__any_sync(0xffffffffu, nslow != 0u)) sweep_redo_slow<G, V, BIAS>(a, row, begin, len, maxlen, have, lane);
 
   if (have) {
     float4 *dst = reinterpret_cast<float4 *>(out < a.R ? a.T + (size_t)out * a.ld
@@ -439,14 +515,16 @@ __global__ void __launch_bounds__(kUpdateWarps * 32) combine_kernel(const Combin
 // xi/eta step (hgaprec.cc:1398-1414, gpbase.hh:877-925), the bias step
 // (hgaprec.cc:1388-1396) and the next iteration's shifted exponentials.
 //
-// Per iteration only what the NEXT iteration reads is stored: A (sweep operand),
-// Elog (exact fallback) and shape.  The rate is rank-2 structured -- rate_uk =
-// E[xi_u] + sum_i E[beta_ik] (hier) or a K-vector (GR) -- so the kernel keeps its
-// two terms (rate_row[r], rate_col[k]) instead of an R x K matrix,
-// and E[v] = shape / rate is only needed by the report-window consumers
-// (held-out ll, top-N, ELBO, hpf_get_state): derive_kernel materialises rate and
-// E[v] from shape and the two terms on demand, with the same fp32 operations, so
-// the values are the ones this kernel used for its row / column sums.
+// Per iteration only what the NEXT iteration reads is stored: A (the sweep
+// operand) and the shape.  The rate is rank-2 structured -- rate_uk = E[xi_u] +
+// sum_i E[beta_ik] (hier) or a K-vector (GR) -- so the kernel keeps its two terms
+// (rate_row[r], rate_col[k]) instead of an R x K matrix; E[v] =
+// shape / rate and E[log v] = psi(shape) - log(rate) are only needed by the
+// report-window consumers (held-out ll, top-N, ELBO, hpf_get_state) and by the
+// exact fallback: derive_kernel materialises rate, E[v] and E[log v] from the
+// shape and the two terms on demand, and the fallback recomputes the E[log v] it
+// needs (load_elog4) -- all with the same fp32 operations, so the values are the
+// ones this kernel used for its row / column sums and its shifted exponentials.
 // ---------------------------------------------------------------------------
 struct UpdateArgs {
   uint32_t R, K, Kp, K4, ld4; // Kp: K rounded up to 4; K4 = Kp / 4; ld4: row stride in float4
@@ -454,11 +532,11 @@ struct UpdateArgs {
   float4 *Tdirect;
   const uint32_t *direct_flag;
   const float *direct_flag_all;        // multi-GPU exact mode: the all-reduced item-side flag (or nullptr)
-  float4 *A, *Elog, *shape;
+  float4 *A, *shape;
   float *shift;                        // [R]
   int hier;
   const float *colsum_other;           // [Kp]  sum over the OTHER side's rows of Ev
-  float *rate_vec;                     // [Kp]  GR: the rate vector (written by block 0); hier: unused
+  float *rate_vec;                     // [Kp]  written by block 0 -- GR: the rate vector; hier: a copy of colsum_other
   float *rate_row;                     // [R]   hier: the E[xi] / E[eta] this update used
   float prior_shape, prior_rate;
   float *pr_shape, *pr_rate, *pr_Ev;   // GPArray xi / eta (hier)
@@ -488,8 +566,6 @@ __device__ __forceinline__ float warp_max(float v)
   return v;
 }
 
-__device__ __forceinline__ float floor30(float v) { return v > 0.f ? v : 1e-30f; } // make_nonzero, gpbase.hh:27-44
-
 __device__ __forceinline__ float &f4at(float4 &v, int j) { return reinterpret_cast<float *>(&v)[j]; }
 __device__ __forceinline__ float f4get(const float4 &v, int j) { return reinterpret_cast<const float *>(&v)[j]; }
 
@@ -504,10 +580,11 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
   const bool use_direct = *a.direct_flag != 0u || (a.direct_flag_all != nullptr && *a.direct_flag_all != 0.f);
   const uint32_t warps_total = gridDim.x * kUpdateWarps;
 
-  // the global-rate (GPMatrixGR) vector is written once, by block 0
-  if (!a.hier && blockIdx.x == 0)
+  // block 0 keeps the column term of the rate for derive_kernel: the global-rate (GPMatrixGR) vector itself, or
+  // (hier) the column sums this update used
+  if (blockIdx.x == 0)
     for (uint32_t k = threadIdx.x; k < a.Kp; k += blockDim.x)
-      a.rate_vec[k] = k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f;
+      a.rate_vec[k] = a.hier ? a.colsum_other[k] : (k < a.K ? a.prior_rate + a.colsum_other[k] : 1.f);
 
   // this lane's columns: the rate's column term and the running column sums stay in registers
   float4 cterm[V], csum[V];
@@ -564,7 +641,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
           if (use_direct) s += f4get(td, j);
           const float rt = rprior + f4get(cterm[v], j);
           const float sa = floor30(s), rb = floor30(rt);
-          const float ev = sa / rb;
+          const float ev = __fdividef(sa, rb); // 2 ulp: feeds the row / column sums only (derive_kernel repeats it)
           const float e = digammaf(sa) - logf(rb);
           f4at(sh, j) = s;
           f4at(el[v], j) = e;
@@ -577,7 +654,6 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
         }
       }
       a.shape[base + q] = sh;
-      a.Elog[base + q] = el[v];
     }
     mx = warp_max(mx);
     rowsum = warp_sum(rowsum);
@@ -658,7 +734,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
 struct DeriveArgs {
   uint32_t R, K, K4, ld4;
   const float4 *shape;
-  float4 *Ev, *rate;        // rate: [R x ld] (hier) or nullptr
+  float4 *Ev, *Elog, *rate; // rate: [R x ld] (hier) or nullptr
   int hier;
   const float *rate_row;    // [R]   hier
   const float *rate_col;    // [Kp]  hier: the column sums the update used; GR: the rate vector
@@ -672,45 +748,50 @@ __global__ void __launch_bounds__(256) derive_kernel(const DeriveArgs a)
     const float4 sh = a.shape[o];
     const float4 ct = __ldg(reinterpret_cast<const float4 *>(a.rate_col) + q);
     const float rr = a.hier ? __ldg(a.rate_row + r) : 0.f;
-    float4 ev, rt;
+    float4 ev, rt, el;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (q * 4 + j < a.K) {
         const float t = a.hier ? rr + f4get(ct, j) : f4get(ct, j);
+        const float sa = floor30(f4get(sh, j)), rb = floor30(t);
         f4at(rt, j) = t;
-        f4at(ev, j) = floor30(f4get(sh, j)) / floor30(t);
+        f4at(ev, j) = __fdividef(sa, rb); // the operation update_kernel used for its sums
+        f4at(el, j) = digammaf(sa) - logf(rb);
       } else {
         f4at(rt, j) = 1.f;
         f4at(ev, j) = 0.f;
+        f4at(el, j) = -CUDART_INF_F;
       }
     }
     a.Ev[o] = ev;
+    a.Elog[o] = el;
     if (a.rate != nullptr) a.rate[o] = rt;
   }
 }
 
 // colsum[k] = sum over blocks of partial[b][k], accumulated in double in a fixed
-// order (one block per 32 columns, 8 row groups per block); also clears the side's
+// order (one block per 32 columns, 32 row groups per block); also clears the side's
 // direct_flag for the next iteration.  Multi-GPU bookkeeping of the exact fallback
 // (one thread): flag_out[0] = 1.0 if *flag_in is set (the theta update publishes the
 // ITEM side's flag into the tail of the reduce block), sticky[0] += reduced[0] (the
 // beta update accumulates the all-reduced flag; read by hpf_iterate at its end).
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
+constexpr int kFinalizeGroups = 32;
+__global__ void __launch_bounds__(32 * kFinalizeGroups) colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
                                                              float *colsum, uint32_t *direct_flag, const uint32_t *flag_in,
                                                              float *flag_out, const float *reduced, float *sticky)
 {
-  __shared__ double part[8][32];
+  __shared__ double part[kFinalizeGroups][32];
   const uint32_t kx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const uint32_t k = blockIdx.x * 32 + kx;
   double s = 0.0;
   if (k < Kp)
-    for (uint32_t b = g; b < nblocks; b += 8) s += (double)partial[(size_t)b * Kp + k];
+    for (uint32_t b = g; b < nblocks; b += kFinalizeGroups) s += (double)partial[(size_t)b * Kp + k];
   part[g][kx] = s;
   __syncthreads();
   if (g == 0 && k < Kp) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += part[q][kx];
+    for (int q = 0; q < kFinalizeGroups; ++q) t += part[q][kx];
     colsum[k] = (float)t;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -898,16 +979,16 @@ __global__ void sum_blocks_kernel(const double *block_sums, uint32_t nblocks, do
 // The orderings are built with cub stable radix sorts of a permutation; these
 // kernels produce the keys and apply the permutation.
 // ---------------------------------------------------------------------------
-__global__ void expand_rows_kernel(const uint64_t *row_ptr, uint32_t nrows, uint64_t nnz, uint32_t *row_of)
+// row_of[j] = the row whose range [row_ptr[r], row_ptr[r + 1]) holds position j.  One warp per row (grid-stride),
+// coalesced stores -- a binary search per nonzero costs 19 dependent loads each at Netflix scale (1.1 ms vs 0.2 ms)
+__global__ void __launch_bounds__(256) expand_rows_kernel(const uint64_t *row_ptr, uint32_t nrows, uint64_t nnz, uint32_t *row_of)
 {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nnz) return;
-  uint32_t lo = 0, hi = nrows; // largest r with row_ptr[r] <= j
-  while (hi - lo > 1) {
-    const uint32_t mid = lo + (hi - lo) / 2;
-    if (row_ptr[mid] <= j) lo = mid; else hi = mid;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+    const uint64_t b = row_ptr[r], e = min(row_ptr[r + 1], nnz);
+    for (uint64_t j = b + lane; j < e; j += 32) row_of[j] = (uint32_t)r;
   }
-  row_of[j] = lo;
 }
 
 __global__ void iota_kernel(uint32_t *p, uint64_t n)
@@ -916,25 +997,38 @@ __global__ void iota_kernel(uint32_t *p, uint64_t n)
   if (j < n) p[j] = (uint32_t)j;
 }
 
-// sort key and payload of one nonzero for an orientation: key = tile(col) * R + row, payload = col | y << 32.
-// One stable radix sort of (key, payload) orders the nonzeros by (tile, row) and carries the gathered-side
-// index and the rating along -- no permutation to chase afterwards.
-__global__ void orient_key_kernel(const uint32_t *row, const uint32_t *col, const uint8_t *y, uint32_t tile_cols, uint32_t R,
-                                  uint64_t nnz, uint32_t *key, uint64_t *val)
+// sort key and payload of one nonzero for an orientation: key = tile(col) * R + row, payload = its position.  One
+// stable radix sort of (key, position) orders the nonzeros by (tile, row); orient_gather_kernel then fetches the
+// gathered-side index and the rating through the sorted positions.  The ratings are not needed before that second
+// step, so their host->device copy runs under the sort (hpf_set_ratings_csr uploads them last, on a second stream).
+__global__ void orient_key_kernel(const uint32_t *row, const uint32_t *col, uint32_t tile_cols, uint32_t R, uint64_t nnz,
+                                  uint32_t *key, uint32_t *pos)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
-  const uint32_t cc = col[j];
-  key[j] = (cc / tile_cols) * R + row[j];
-  val[j] = (uint64_t)cc | ((uint64_t)(y != nullptr ? y[j] : 1u) << 32);
+  key[j] = (col[j] / tile_cols) * R + row[j];
+  pos[j] = (uint32_t)j;
 }
-__global__ void orient_unpack_kernel(const uint64_t *val, uint64_t nnz, uint32_t *out_idx, uint8_t *out_y)
+// pack != 0: one word per nonzero for the sweep, index | rating << 24 (the gathered side has < 2^24 rows)
+__global__ void orient_gather_kernel(const uint32_t *pos, const uint32_t *col, const uint8_t *y, uint64_t nnz, uint32_t *out_idx,
+                                     uint8_t *out_y, int pack)
 {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
-  const uint64_t v = val[j];
-  out_idx[j] = (uint32_t)v;
-  if (out_y != nullptr) out_y[j] = (uint8_t)(v >> 32);
+  const uint32_t p = pos[j];
+  const uint32_t cc = col[p];
+  if (pack) {
+    out_idx[j] = cc | ((y != nullptr ? (uint32_t)y[p] : 1u) << 24);
+  } else {
+    out_idx[j] = cc;
+    if (out_y != nullptr) out_y[j] = y[p];
+  }
+}
+// the same packing for an orientation that needs no sort (the CSR as given)
+__global__ void pack_kernel(const uint32_t *idx, const uint8_t *y, uint64_t nnz, uint32_t *out)
+{
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) out[j] = idx[j] | ((y != nullptr ? (uint32_t)y[j] : 1u) << 24);
 }
 
 // run_ptr[c] = first position whose sorted key is >= c, for c in [0, nkeys]

@@ -561,9 +561,10 @@ topn_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
 // ---------------------------------------------------------------------------
 constexpr int kRankWarps = 8;          // rank_prep_kernel: users per CTA
 constexpr int kQBatch = 32;            // queries of a row per pass
-constexpr int kRankEpiWarps = 8;       // rank_mma_kernel: two epilogue threads per row, half of a tile's columns each
+constexpr int kRankEpiWarps = 16;      // rank_mma_kernel: four epilogue threads per row, a quarter of a tile's columns each
+constexpr int kRankColsPerThread = kTileN / (kRankEpiWarps / 4);
 constexpr int kRankThreads = 64 + 32 * kRankEpiWarps;
-constexpr uint32_t kRankKeyBytes = kQBatch * kTileM * 8;         // sorted query keys      [slot][row]
+constexpr uint32_t kRankKeyBytes = kQBatch * kTileM * 8;         // sorted query keys: score words [slot][row], then item words [slot][row]
 constexpr uint32_t kRankHistBytes = (kQBatch + 1) * kTileM * 4;  // counts per bucket      [bucket][row]
 constexpr uint32_t kRankOrigBytes = kQBatch * kTileM;            // query index in the batch, self flag: [slot][row] bytes
 constexpr uint32_t kRankSmemBytes = 1024 + kStageBytes + kRankKeyBytes + kRankHistBytes + 2 * kRankOrigBytes + 256;
@@ -618,7 +619,8 @@ rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
-  unsigned long long *qkey = reinterpret_cast<unsigned long long *>(gen_base + kStageBytes);         // [kQBatch][128]
+  uint32_t *qhi = reinterpret_cast<uint32_t *>(gen_base + kStageBytes);                               // [kQBatch][128] score words
+  uint32_t *qlo = qhi + kQBatch * kTileM;                                                             // [kQBatch][128] ~item
   uint32_t *hist = reinterpret_cast<uint32_t *>(gen_base + kStageBytes + kRankKeyBytes);             // [kQBatch + 1][128]
   uint8_t *qorig = gen_base + kStageBytes + kRankKeyBytes + kRankHistBytes;                           // [kQBatch][128]
   uint8_t *selfgt = qorig + kRankOrigBytes;                                                           // [kQBatch][128]
@@ -692,10 +694,10 @@ rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
     }
   } else {
-    // ===== epilogue: two threads per user row, each half of every tile's columns =====
-    const int ew = warp - 2;                       // 0..7
+    // ===== epilogue: four threads per user row, each a quarter of every tile's columns =====
+    const int ew = warp - 2;                       // 0..15
     const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                      // which half of the columns (warps 2-5: the quarter order is 2,3,0,1 twice)
+    const int half = ew >> 2;                      // which part of the columns (the quarter order is 2,3,0,1 in every group of four warps)
     const uint32_t r_in = (uint32_t)(q4 * 32 + lane);
     const uint32_t row = tile_m * kTileM + r_in;
     const bool live = row < a.nu;
@@ -715,17 +717,20 @@ rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       if (half == 0) {
         // this row's batch: keys ascending by insertion (<= 32 of them), unused slots = +inf; counts cleared
         for (uint32_t j = 0; j < (uint32_t)kQBatch; ++j) {
-          unsigned long long k = j < nq ? a.q_key[b0 + j] : ~0ull;
-          uint32_t o = j;
+          const unsigned long long k = j < nq ? a.q_key[b0 + j] : ~0ull;
           // insert into the sorted prefix [0, j)
           uint32_t p = j;
-          while (p > 0 && qkey[(p - 1) * kTileM + r_in] > k) {
-            qkey[p * kTileM + r_in] = qkey[(p - 1) * kTileM + r_in];
+          while (p > 0) {
+            const unsigned long long prev = ((unsigned long long)qhi[(p - 1) * kTileM + r_in] << 32) | qlo[(p - 1) * kTileM + r_in];
+            if (prev <= k) break;
+            qhi[p * kTileM + r_in] = qhi[(p - 1) * kTileM + r_in];
+            qlo[p * kTileM + r_in] = qlo[(p - 1) * kTileM + r_in];
             qorig[p * kTileM + r_in] = qorig[(p - 1) * kTileM + r_in];
             --p;
           }
-          qkey[p * kTileM + r_in] = k;
-          qorig[p * kTileM + r_in] = (uint8_t)o;
+          qhi[p * kTileM + r_in] = (uint32_t)(k >> 32);
+          qlo[p * kTileM + r_in] = (uint32_t)k;
+          qorig[p * kTileM + r_in] = (uint8_t)j;
           selfgt[j * kTileM + r_in] = 0;
         }
         for (uint32_t b = 0; b <= (uint32_t)kQBatch; ++b) hist[b * kTileM + r_in] = 0u;
@@ -733,28 +738,29 @@ rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kRankEpiWarps) : "memory");
       uint32_t excur = 0;
       for (uint32_t j = 0; j < a.ntiles_n; ++j, ++jt) {
-        const uint32_t col0 = j * kTileN + (uint32_t)half * (kTileN / 2);
+        constexpr uint32_t kCols = (uint32_t)kRankColsPerThread;
+        const uint32_t col0 = j * kTileN + (uint32_t)half * kCols;
         const uint32_t lim = a.m > col0 ? a.m - col0 : 0u;
-        const uint32_t ncols = lim < (uint32_t)(kTileN / 2) ? lim : (uint32_t)(kTileN / 2);
-        uint32_t mask[kTileN / 64];
+        const uint32_t ncols = lim < kCols ? lim : kCols;
+        uint32_t mask[kCols / 32];
 #pragma unroll
-        for (int w = 0; w < kTileN / 64; ++w) mask[w] = 0u;
+        for (uint32_t w = 0; w < kCols / 32; ++w) mask[w] = 0u;
         while (excur < exlen) { // the sorted exclusion list, restricted to this thread's columns of the tile
           const uint32_t v = __ldg(ex + excur);
-          if (v >= col0 + (uint32_t)(kTileN / 2)) break;
+          if (v >= col0 + kCols) break;
           if (v >= col0) {
             const uint32_t o = v - col0, bit = 1u << (o & 31u);
 #pragma unroll
-            for (int w = 0; w < kTileN / 64; ++w) mask[w] |= ((o >> 5) == (uint32_t)w) ? bit : 0u;
+            for (uint32_t w = 0; w < kCols / 32; ++w) mask[w] |= ((o >> 5) == w) ? bit : 0u;
           }
           ++excur;
         }
         mbar_wait(bar_tfull, jt & 1u);
         tc_fence_after();
 #pragma unroll
-        for (uint32_t c = 0; c < kTileN / 64; ++c) {
+        for (uint32_t c = 0; c < kCols / 32; ++c) {
           uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * (kTileN / 2) + c * 32, r);
+          tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * kCols + c * 32, r);
           tc_wait_ld();
           const uint32_t valid = ncols > c * 32 ? ncols - c * 32 : 0u;
           const uint32_t mw = mask[c];
@@ -763,21 +769,22 @@ rank_mma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if ((uint32_t)i >= valid) continue; // only the last tile has columns past the last item
-              uint32_t bits = ((mw >> i) & 1u) ? 0u : r[i];
-              if ((int)bits < 0) bits = 0u;
-              const unsigned long long x = ((unsigned long long)bits << 32) | (unsigned long long)(inv0 - (uint32_t)i);
-              // b = number of batch keys smaller than x: 5-step search over the 32 sorted slots (pads are +inf)
+              uint32_t xhi = ((mw >> i) & 1u) ? 0u : r[i];
+              if ((int)xhi < 0) xhi = 0u;
+              const uint32_t xlo = inv0 - (uint32_t)i;
+              // b = number of batch keys smaller than x = (xhi, xlo).  First by score word alone (32-bit compares): a
+              // 5-step search over the 32 sorted slots plus the 6th comparison 32 slots need; then the (rare) run
+              // of keys with the SAME score word is walked comparing item words.  Pads are +inf.
               uint32_t b = 0;
 #pragma unroll
               for (uint32_t step = kQBatch / 2; step >= 1; step >>= 1)
-                if (qkey[(b + step - 1) * kTileM + r_in] < x) b += step;
-              if (b < (uint32_t)kQBatch && qkey[b * kTileM + r_in] < x) ++b; // 32 slots need a 6th comparison
-              atomicAdd(hist + b * kTileM + r_in, 1u); // the row's other thread counts into the same table
+                if (qhi[(b + step - 1) * kTileM + r_in] < xhi) b += step;
+              if (qhi[b * kTileM + r_in] < xhi) ++b;
+              while (b < (uint32_t)kQBatch && qhi[b * kTileM + r_in] == xhi && qlo[b * kTileM + r_in] < xlo) ++b;
+              atomicAdd(hist + b * kTileM + r_in, 1u); // the row's other threads count into the same table
               // the query item itself, with the tensor-core score: next to the insertion point.  It must not count
               // towards its own rank, whichever of its two scores is larger.
-              const uint32_t xlo = (uint32_t)x;
-              if (b < (uint32_t)kQBatch && (uint32_t)qkey[b * kTileM + r_in] == xlo) { /* key_q >= x: not counted anyway */ }
-              else if (b > 0 && (uint32_t)qkey[(b - 1) * kTileM + r_in] == xlo) selfgt[(b - 1) * kTileM + r_in] = 1; // x > key_q
+              if (b > 0 && qlo[(b - 1) * kTileM + r_in] == xlo) selfgt[(b - 1) * kTileM + r_in] = 1; // x > key_q: counted, take it out
             }
           }
         }

@@ -249,14 +249,17 @@ def test_default_plan_is_bitwise_deterministic(flags, dense):
             np.testing.assert_array_equal(a.p[gname][f], b.p[gname][f])
 
 
-@pytest.mark.parametrize("seg_len,tile_kb,dense", [("64", None, "0"), ("8", None, "0"), ("64", 300, "0"), ("64", None, "1"),
-                                                   ("16", 150, "1")])
+@pytest.mark.parametrize("seg_len,tile_kb,dense,pack", [("64", None, "0", "1"), ("8", None, "0", "1"), ("64", 300, "0", "1"),
+                                                        ("64", None, "1", "1"), ("16", 150, "1", "1"), ("64", None, "0", "0"),
+                                                        ("16", 150, "1", "0")])
 @pytest.mark.parametrize("flags", [H.HIER, H.BIAS])
-def test_every_sweep_plan_matches_oracle(monkeypatch, flags, seg_len, tile_kb, dense):
+def test_every_sweep_plan_matches_oracle(monkeypatch, flags, seg_len, tile_kb, dense, pack):
     """The device-built work lists in every shape they take: short segments (rows split over many partial slots and
     combined in a fixed order), L2-tiled orderings of both passes, with and without the dense tcgen05 head (whose
-    items have no rows in the item pass and no nonzeros in the user pass)."""
+    items have no rows in the item pass and no nonzeros in the user pass), with index and rating packed into one word
+    per nonzero (the default whenever the gathered side has < 2^24 rows) and in separate streams."""
     monkeypatch.setenv("HPF_DENSE_HEAD", dense)
+    monkeypatch.setenv("HPF_PACK", pack)
     monkeypatch.setenv("HPF_SEG_LEN", seg_len)
     if tile_kb:
         monkeypatch.setenv("HPF_L2_TILE_KB", str(tile_kb))

@@ -41,6 +41,7 @@ with H.Engine(n, m, k, flags=H.HIER) as e:
     t0 = time.time()
     ranks, rscores = e.item_ranks(users, d["row_ptr"], d["col_idx"], qp, qi)
     dt_rank = time.time() - t0
+    rank_kernel_ms = e.stats()["last_topn_ms"]
     for u in (0, n // 3, n - 1):
         sc = (Et[u] @ Eb.T).astype(np.float32)
         sc[d["col_idx"][int(d["row_ptr"][u]):int(d["row_ptr"][u + 1])]] = 0
@@ -50,7 +51,7 @@ with H.Engine(n, m, k, flags=H.HIER) as e:
             ok &= abs(int(ranks[u * nq + j]) - want_rank) <= 2      # fp32 summation order near ties
 flop = 2.0 * n * m * k
 print(json.dumps({"item_ranks": {"what": "hpf_item_ranks, all users, %d queries each, host in/out" % nq, "seconds": dt_rank,
-                                 "queries": int(n * nq)}, "what": "hpf_topn, all users, top-100, host in/out", "users": n, "items": m, "k": k, "excluded": int(len(d["col_idx"])),
+                                 "kernel_ms": rank_kernel_ms, "queries": int(n * nq)}, "what": "hpf_topn, all users, top-100, host in/out", "users": n, "items": m, "k": k, "excluded": int(len(d["col_idx"])),
                   "seconds": dt, "kernel_ms": kernel_ms, "kernel_algorithmic_tflops": flop / (kernel_ms * 1e-3) / 1e12,
                   "kernel_issued_tflops_bf16": 3 * 2.0 * n * (-(-m // 256) * 256) * 128 / (kernel_ms * 1e-3) / 1e12,
                   "algorithmic_tflops": flop / dt / 1e12, "scores_per_s": n * m / dt, "spot_check_ok": ok}))
