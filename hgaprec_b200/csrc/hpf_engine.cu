@@ -1542,7 +1542,7 @@ void state_arrays(hpf_ctx *c, std::vector<std::pair<void *, size_t>> *v)
   for (int side = 0; side < 2; ++side) {
     Side &s = side == 0 ? c->th : c->be;
     const size_t rk = (size_t)s.R * c->ld * sizeof(float), rv = (size_t)s.R * sizeof(float);
-    v->emplace_back(s.A, rk); v->emplace_back(s.Elog, rk); v->emplace_back(s.shape, rk);
+    v->emplace_back(s.A, rk); v->emplace_back(s.shape, rk); // rate, E[v], E[log v]: not written inside a window
     v->emplace_back(s.shift, rv); v->emplace_back(s.rate_col, c->Kp * sizeof(float));
     if (c->hier) {
       v->emplace_back(s.rate_row, rv); v->emplace_back(s.pr_shape, rv); v->emplace_back(s.pr_rate, rv); v->emplace_back(s.pr_Ev, rv);
@@ -1613,7 +1613,10 @@ int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
       // only.  Re-run the window from the snapshot with the fallback buffers inside the all-reduce, and stay there.
       c->mg_exact = true;
       TRY(snapshot_state(c, true));
-      c->th.derived_valid = sv.th_valid && false; c->be.derived_valid = sv.be_valid && false; // Ev / rate are re-derived on demand
+      // rate, E[v] and E[log v] are never written inside a window (only derive_kernel and hpf_set_state write them): if
+      // they were current when the window began they still are -- and after hpf_set_state they are NOT functions of
+      // the shape (src/gpbase.hh:324-340), so the fallback of the first iteration must read them, not recompute them
+      c->th.derived_valid = sv.th_valid; c->be.derived_valid = sv.be_valid;
       c->pr_prev_valid = sv.pr_prev_valid; c->th_colsum_global = sv.th_global; c->iterations = sv.iterations;
       c->dense.a_dirty = true;
       const float first_ms = c->last_ms;
