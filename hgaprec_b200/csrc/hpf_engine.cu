@@ -221,7 +221,7 @@ struct hpf_ctx {
   int rank = 0, nranks = 1;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_chunk[kMaxChunks] = { nullptr }, ev_theta = nullptr, ev_comm = nullptr;
-  int ar_chunks = -1;             // HPF_AR_CHUNKS: chunks of the item pass (-1: from the payload size)
+  int ar_chunks = -1;             // HPF_AR_CHUNKS: chunks of the item pass (unset: one; see hpf_set_ratings_csr)
   // A nonzero that takes the exact fallback adds to the rank-local Tdirect buffers; on the item side those would
   // have to be summed over the ranks too.  That never happens in a real fit, so the reduction is
   // optimistic: the ranks agree on a "fallback fired" flag that rides with the column sums, and hpf_iterate re-runs
@@ -919,14 +919,29 @@ int item_pass(hpf_ctx *c)
   for (uint32_t q = 0; q < w.nchunks; ++q) {
     TRY(launch_sweep(c, c->be, c->th, (int)q)); // CSC rows = items of chunk q: T_beta (local users only)
     TRY(launch_combine(c, c->be, (int)q));
-    if (mg) { // rows [r0, r1) of T_beta are final on this rank: sum them over the ranks under what follows
-      const size_t r0 = (size_t)q * w.chunk_rows, r1 = std::min<size_t>((size_t)(q + 1) * w.chunk_rows, c->be.R);
-      CU(cudaEventRecord(c->ev_chunk[q], c->stream));
-      CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[q], 0));
-      TRY(comm_allreduce(c, c->be.T + r0 * c->ld, (r1 - r0) * c->ld));
-    }
+    if (mg) CU(cudaEventRecord(c->ev_chunk[q], c->stream)); // rows of chunk q are final on this rank from here on
   }
   STAGE_END(1);
+  return 0;
+}
+
+// The collectives of one iteration, issued after every compute kernel up to the theta update has been enqueued, so
+// the host never sits in an NCCL call while the compute stream runs dry.  On the device comm_stream waits for each
+// chunk's event, so chunk q's all-reduce runs under whatever the compute stream does after that chunk.
+int issue_collectives(hpf_ctx *c)
+{
+  const WorkList &w = c->be.wl;
+  for (uint32_t q = 0; q < w.nchunks; ++q) {
+    const size_t r0 = (size_t)q * w.chunk_rows, r1 = std::min<size_t>((size_t)(q + 1) * w.chunk_rows, c->be.R);
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[q], 0));
+    TRY(comm_allreduce(c, c->be.T + r0 * c->ld, (r1 - r0) * c->ld));
+  }
+  // [Tb_beta | sum_u E[theta] | fallback flag] summed over the user shards; with mg_exact also the item side's
+  // fallback buffers [Tdirect_beta | Tbdirect_beta]
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_theta, 0));
+  TRY(comm_allreduce(c, c->red_tail, c->red_tail_count));
+  if (c->mg_exact) TRY(comm_allreduce(c, c->redblock2, c->red2_count));
+  CU(cudaEventRecord(c->ev_comm, c->comm_stream));
   return 0;
 }
 
@@ -968,13 +983,8 @@ int one_iteration(hpf_ctx *c)
   STAGE_END(4);
   STAGE_BEGIN(5);
   if (mg) {
-    // [Tb_beta | sum_u E[theta] | fallback flag] summed over the user shards; with mg_exact also the item side's
-    // fallback buffers [Tdirect_beta | Tbdirect_beta]
     CU(cudaEventRecord(c->ev_theta, c->stream));
-    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_theta, 0));
-    TRY(comm_allreduce(c, c->red_tail, c->red_tail_count));
-    if (c->mg_exact) TRY(comm_allreduce(c, c->redblock2, c->red2_count));
-    CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+    TRY(issue_collectives(c));
     CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
     c->th_colsum_global = true;
   }
@@ -1185,13 +1195,15 @@ int hpf_set_ratings_csr(hpf_ctx *c, const uint64_t *row_ptr, const uint32_t *col
   const uint32_t th_t = tiles_for(c, m, n, nnz), be_t = tiles_for(c, n, m, nnz);
   const bool try_dense = c->dense_head_mode != 0 && c->Kp + (c->bias ? 2u : 0u) <= (uint32_t)head::kFact && nnz > 0;
   c->dense.on = false;
-  // chunks of the item pass (multi-GPU: one all-reduce per chunk, overlapped with the following sweeps).  A chunk
-  // should carry tens of MB so that the collective runs at bandwidth, and a launch per chunk must stay cheap.
+  // Chunks of the item pass (multi-GPU): with C > 1 chunks the all-reduce of a finished chunk's T_beta rows starts under
+  // the next chunk's sweep.  Measured (MSD scale, 307 MB payload) that does not pay, wherever the host issues the calls
+  // from: the item sweep is HBM-bound and NCCL's reduce/copy CTAs take bandwidth and SMs from it, so the sweep loses
+  // about what the all-reduce gains (8 x B200: item pass 0.71 / 1.27 / 2.39 ms with 1 / 3 / 6 chunks, iteration 2.67 /
+  // 2.74 / 3.69 ms, profiles/r02p_bench_n8_msd*.json; 2 x B200 with the calls deferred: 6.47 vs 6.81 ms,
+  // profiles/r02q_*).  One chunk, whose all-reduce runs under the user pass and the theta update, is the default;
+  // HPF_AR_CHUNKS keeps the pipelined form available (and tested).
   uint32_t item_chunks = 1;
-  if (c->nranks > 1) {
-    const uint64_t payload = (uint64_t)m * c->ld * sizeof(float);
-    item_chunks = c->ar_chunks > 0 ? (uint32_t)c->ar_chunks : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, payload / (48ull << 20)));
-  }
+  if (c->nranks > 1 && c->ar_chunks > 0) item_chunks = (uint32_t)c->ar_chunks;
   size_t cub_bytes = 0, scan_bytes = 0;
   const uint64_t seg_bound = std::max(worklist_seg_bound(nnz, n, th_t, L), worklist_seg_bound(nnz, m, be_t, L));
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint64_t *)nullptr,
