@@ -523,7 +523,7 @@ def main():
                            "l2_policy": "inputs larger than L2 (ratings %.0f MB + factor rows %.0f MB per GPU vs 126 MB L2)"
                                         % ((2 * r["nnz"] * 5) / 1e6, (r["n"] + r["m"]) * k * 4 * 2 / 1e6),
                            "sweep_group": stats["sweep_group"], "sweep_vec": stats["sweep_vec"],
-                           "item_chunks": stats["item_chunks"], "extra_untimed_warmup_steps": EXTRA_WARMUP,
+                           "item_chunks": stats["item_chunks"], "beta_sharded": stats["beta_sharded"], "extra_untimed_warmup_steps": EXTRA_WARMUP,
                            "sweep_plan": ("gather kernel on both passes" if not stats["head_nnz"] else
                                           "gather kernel for the tail + dense tcgen05 head (%d nonzeros of the most popular items)"
                                           % stats["head_nnz"]),

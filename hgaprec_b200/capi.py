@@ -49,7 +49,7 @@ class Stats(ctypes.Structure):
                 ("last_iterate_ms", ctypes.c_float), ("sweep_group", ctypes.c_uint32), ("sweep_vec", ctypes.c_uint32),
                 ("user_l2_tiles", ctypes.c_uint32), ("item_l2_tiles", ctypes.c_uint32), ("head_nnz", ctypes.c_uint64),
                 ("item_chunks", ctypes.c_uint32), ("mg_exact", ctypes.c_uint32), ("last_topn_ms", ctypes.c_float),
-                ("n_devices", ctypes.c_uint32)]
+                ("n_devices", ctypes.c_uint32), ("beta_sharded", ctypes.c_uint32)]
 
 
 class IterProfile(ctypes.Structure):

@@ -73,6 +73,10 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool load(std::string &err)
@@ -88,6 +92,10 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
     CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
     AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+    ReduceScatter = (decltype(ReduceScatter))dlsym(handle, "ncclReduceScatter");
+    AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
+    GroupStart = (decltype(GroupStart))dlsym(handle, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(handle, "ncclGroupEnd");
     CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
     GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "libnccl lacks expected symbols"; return false; }
@@ -128,6 +136,7 @@ constexpr uint32_t kMaxHeadBlocks = 4;
 constexpr uint32_t kElboLaunches = 7; // nnz, theta, beta, xi, eta, theta bias, beta bias
 
 constexpr uint32_t kMaxChunks = 16;
+constexpr uint32_t kRowPad = HPF_MAX_DEVICES; // spare rows of the arrays the sharded beta update scatters / gathers in place
 struct WorkList {       // segments of one orientation: (chunk of rows, L2 tile, descending length)
   uint4 *seg = nullptr;
   uint32_t *seg_out = nullptr;
@@ -221,12 +230,23 @@ struct hpf_ctx {
   int rank = 0, nranks = 1;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_chunk[kMaxChunks] = { nullptr }, ev_theta = nullptr, ev_comm = nullptr;
+  bool ar_defer = false;          // HPF_AR_DEFER (experiments): chunked item pass, but no all-reduce before its last chunk
   int ar_chunks = -1;             // HPF_AR_CHUNKS: chunks of the item pass (unset: one; see hpf_set_ratings_csr)
   // A nonzero that takes the exact fallback adds to the rank-local Tdirect buffers; on the item side those would
   // have to be summed over the ranks too.  That never happens in a real fit, so the reduction is
   // optimistic: the ranks agree on a "fallback fired" flag that rides with the column sums, and hpf_iterate re-runs
   // its window from a snapshot with the fallback buffers inside the all-reduce (mg_exact, sticky) when it is set.
   bool mg_exact = false;
+  // Sharded beta update (multi-GPU, many items): T_beta is reduce-SCATTERED, each rank updates its slice of
+  // ceil(m / N) items, and only A_beta -- all the sweeps read -- is all-gathered every iteration; the rest of beta's
+  // state (shape, xi/eta terms, shift) is gathered when the window of hpf_iterate ends, so every other entry point
+  // sees whole arrays.  Inside a window the exact fallback would read stale rows of them: ANY fallback (user or item
+  // side) raises the flag and the window re-runs unsharded in mg_exact mode.
+  int shard_mode = -1;            // HPF_SHARD_BETA: -1 auto (payload >= kShardMinBytes), 0 off, 1 on
+  bool shard_now = false;         // this window runs sharded
+  bool last_sharded = false;      // ... the last one did (hpf_stats)
+  uint32_t slice_rows = 0;        // ceil(m / N)
+  cudaEvent_t ev_beta = nullptr;
   float *snap = nullptr; size_t snap_cap = 0;
   // stats
   uint64_t launches = 0, iterations = 0;
@@ -341,20 +361,22 @@ int alloc_side(hpf_ctx *c, Side &s, uint32_t R, bool own_direct)
 {
   s.R = R;
   const size_t rk = (size_t)R * c->ld;
-  TRY(dalloc(c, &s.A, rk));
+  // what the sharded beta update gathers in place carries kRowPad spare rows: N equal slices of ceil(R / N) rows
+  const size_t Rg = (size_t)R + kRowPad, rkg = Rg * c->ld;
+  TRY(dalloc(c, &s.A, rkg));
   TRY(dalloc(c, &s.Elog, rk));
   TRY(dalloc(c, &s.Ev, rk));
-  TRY(dalloc(c, &s.shape, rk));
+  TRY(dalloc(c, &s.shape, rkg));
   TRY(dalloc(c, &s.rate, c->hier ? rk : (size_t)c->Kp));
   TRY(dalloc(c, &s.rate_col, c->Kp));
-  if (c->hier) TRY(dalloc(c, &s.rate_row, R));
+  if (c->hier) TRY(dalloc(c, &s.rate_row, Rg));
   if (own_direct) TRY(dalloc(c, &s.Tdirect, rk));
-  TRY(dalloc(c, &s.shift, R));
+  TRY(dalloc(c, &s.shift, Rg));
   TRY(dalloc(c, &s.direct_flag, 1));
   if (c->hier) {
-    TRY(dalloc(c, &s.pr_shape, R));
-    TRY(dalloc(c, &s.pr_rate, R));
-    TRY(dalloc(c, &s.pr_Ev, R));
+    TRY(dalloc(c, &s.pr_shape, Rg));
+    TRY(dalloc(c, &s.pr_rate, Rg));
+    TRY(dalloc(c, &s.pr_Ev, Rg));
     if (c->logl) {
       TRY(dalloc(c, &s.pr_shape_prev, R));
       TRY(dalloc(c, &s.pr_rate_prev, R));
@@ -465,20 +487,25 @@ template <int V> int launch_update_v(hpf_ctx *c, const UpdateArgs &a, uint32_t g
 // dense update of one side.  colsum_other: the other side's column sums of E[v]; bias_count: what the bias rate adds
 // (m for users, n_global for items).  The theta update also publishes the item side's fallback flag next to its
 // column sums (tail of the reduce block); the beta update accumulates the all-reduced flag (multi-GPU).
-int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_count)
+int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_count, uint32_t row0 = 0, uint32_t rows = UINT32_MAX)
 {
   const bool theta = &s == &c->th;
+  if (rows == UINT32_MAX) rows = s.R;
+  const bool slice = rows != s.R; // sharded beta update: rows [row0, row0 + rows) only (never with -bias, never theta)
+  const uint32_t grid = slice ? update_grid_for(c, std::max(rows, 1u)) : s.update_grid;
+  const size_t o = (size_t)row0 * c->ld;
   UpdateArgs a;
   memset(&a, 0, sizeof a);
-  a.R = s.R; a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4; a.ld4 = c->ld / 4;
-  a.T = reinterpret_cast<const float4 *>(s.T); a.Tdirect = reinterpret_cast<float4 *>(s.Tdirect); a.direct_flag = s.direct_flag;
+  a.R = rows; a.K = c->K; a.Kp = c->Kp; a.K4 = c->K4; a.ld4 = c->ld / 4;
+  a.T = reinterpret_cast<const float4 *>(s.T + o); a.Tdirect = reinterpret_cast<float4 *>(s.Tdirect + o); a.direct_flag = s.direct_flag;
   a.direct_flag_all = (!theta && c->mg_exact && c->nranks > 1) ? c->red_flag : nullptr;
-  a.A = reinterpret_cast<float4 *>(s.A); a.shape = reinterpret_cast<float4 *>(s.shape);
-  a.shift = s.shift;
+  a.A = reinterpret_cast<float4 *>(s.A + o); a.shape = reinterpret_cast<float4 *>(s.shape + o);
+  a.shift = s.shift + row0;
   a.hier = c->hier; a.colsum_other = colsum_other;
-  a.rate_vec = s.rate_col; a.rate_row = s.rate_row;
+  a.rate_vec = s.rate_col; a.rate_row = s.rate_row ? s.rate_row + row0 : nullptr;
   a.prior_shape = (float)s.prior_shape; a.prior_rate = (float)s.prior_rate;
-  a.pr_shape = s.pr_shape; a.pr_rate = s.pr_rate; a.pr_Ev = s.pr_Ev;
+  a.pr_shape = s.pr_shape ? s.pr_shape + row0 : nullptr; a.pr_rate = s.pr_rate ? s.pr_rate + row0 : nullptr;
+  a.pr_Ev = s.pr_Ev ? s.pr_Ev + row0 : nullptr;
   a.pr_prior_shape = (float)s.pr_prior_shape; a.pr_prior_rate = (float)s.pr_prior_rate;
   a.bias = c->bias; a.Tb = s.Tb; a.Tbdirect = s.Tbdirect;
   a.b_shape = s.b_shape; a.b_rate = s.b_rate; a.b_Ev = s.b_Ev; a.b_Elog = s.b_Elog; a.aux = s.aux;
@@ -489,22 +516,22 @@ int launch_update(hpf_ctx *c, Side &s, const float *colsum_other, double bias_co
     a.split_hi = c->dense.a_hi; a.split_lo = c->dense.a_lo; a.split_ld = head::kFact;
   }
   s.derived_valid = false;
-  switch ((c->K4 + 31) / 32) {
-  case 1: TRY(launch_update_v<1>(c, a, s.update_grid)); break;
-  case 2: TRY(launch_update_v<2>(c, a, s.update_grid)); break;
-  case 3: TRY(launch_update_v<3>(c, a, s.update_grid)); break;
-  case 4: TRY(launch_update_v<4>(c, a, s.update_grid)); break;
-  case 5: TRY(launch_update_v<5>(c, a, s.update_grid)); break;
-  case 6: TRY(launch_update_v<6>(c, a, s.update_grid)); break;
-  case 7: TRY(launch_update_v<7>(c, a, s.update_grid)); break;
-  case 8: TRY(launch_update_v<8>(c, a, s.update_grid)); break;
+  if (rows > 0) switch ((c->K4 + 31) / 32) {
+  case 1: TRY(launch_update_v<1>(c, a, grid)); break;
+  case 2: TRY(launch_update_v<2>(c, a, grid)); break;
+  case 3: TRY(launch_update_v<3>(c, a, grid)); break;
+  case 4: TRY(launch_update_v<4>(c, a, grid)); break;
+  case 5: TRY(launch_update_v<5>(c, a, grid)); break;
+  case 6: TRY(launch_update_v<6>(c, a, grid)); break;
+  case 7: TRY(launch_update_v<7>(c, a, grid)); break;
+  case 8: TRY(launch_update_v<8>(c, a, grid)); break;
   default: return fail(c, HPF_EINVAL, "unsupported factor count %u", c->K);
   }
   const bool mg = c->nranks > 1;
   colsum_finalize_kernel<<<(c->Kp + 31) / 32, 32 * kFinalizeGroups, 0, c->stream>>>(
-      s.colsum_partial, s.update_grid, c->Kp, s.colsum, s.direct_flag,
-      theta && mg ? c->be.direct_flag : nullptr, theta && mg ? c->red_flag : nullptr,
-      !theta && mg ? c->red_flag : nullptr, !theta && mg ? c->mg_fired : nullptr);
+      s.colsum_partial, rows > 0 ? grid : 0, c->Kp, s.colsum, s.direct_flag,
+      theta && mg ? c->be.direct_flag : nullptr, theta && mg && c->shard_now ? c->th.direct_flag : nullptr,
+      theta && mg ? c->red_flag : nullptr, !theta && mg ? c->red_flag : nullptr, !theta && mg ? c->mg_fired : nullptr);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -538,7 +565,7 @@ int refresh_colsum(hpf_ctx *c, Side &s)
   c->launches++;
   CU(cudaGetLastError());
   colsum_finalize_kernel<<<(c->Kp + 31) / 32, 32 * kFinalizeGroups, 0, c->stream>>>(s.colsum_partial, s.update_grid, c->Kp, s.colsum,
-                                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -866,10 +893,15 @@ int ensure_aux(hpf_ctx *c)
 int comm_streams(hpf_ctx *c) // after c->comm / c->nranks are set
 {
   if (c->nranks > 1 && !c->comm_stream) {
-    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    // highest priority: the collective's few CTAs must get onto the SMs while a sweep grid is still draining
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char *pe = getenv("HPF_COMM_PRIO"); // experiments: 0 = default priority
+    CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, pe && atoi(pe) == 0 ? prio_lo : prio_hi));
     for (auto &e : c->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_theta, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_beta, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -931,9 +963,15 @@ int item_pass(hpf_ctx *c)
 int issue_collectives(hpf_ctx *c)
 {
   const WorkList &w = c->be.wl;
-  for (uint32_t q = 0; q < w.nchunks; ++q) {
+  if (c->shard_now) { // T_beta: every rank keeps the sum of its own slice of items only
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[w.nchunks - 1], 0));
+    const size_t cnt = (size_t)c->slice_rows * c->ld;
+    const int rc = g_nccl.ReduceScatter(c->be.T, c->be.T + (size_t)c->rank * cnt, cnt, ncclFloat32, ncclSum, c->comm, c->comm_stream);
+    if (rc != ncclSuccess) return nccl_fail(c, rc, "ncclReduceScatter");
+  }
+  for (uint32_t q = 0; q < w.nchunks && !c->shard_now; ++q) {
     const size_t r0 = (size_t)q * w.chunk_rows, r1 = std::min<size_t>((size_t)(q + 1) * w.chunk_rows, c->be.R);
-    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[q], 0));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_chunk[c->ar_defer ? w.nchunks - 1 : q], 0));
     TRY(comm_allreduce(c, c->be.T + r0 * c->ld, (r1 - r0) * c->ld));
   }
   // [Tb_beta | sum_u E[theta] | fallback flag] summed over the user shards; with mg_exact also the item side's
@@ -942,6 +980,54 @@ int issue_collectives(hpf_ctx *c)
   TRY(comm_allreduce(c, c->red_tail, c->red_tail_count));
   if (c->mg_exact) TRY(comm_allreduce(c, c->redblock2, c->red2_count));
   CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+  return 0;
+}
+
+// in-place all-gather of an array whose rank-r slice is elements [r * count, (r + 1) * count)
+int comm_allgather(hpf_ctx *c, float *base, size_t count)
+{
+  if (count == 0) return 0;
+  const int rc = g_nccl.AllGather(base + (size_t)c->rank * count, base, count, ncclFloat32, c->comm, c->comm_stream);
+  return rc == ncclSuccess ? 0 : nccl_fail(c, rc, "ncclAllGather");
+}
+
+// sharded beta update: does this window qualify?  Every input is the same on all ranks.
+constexpr uint64_t kShardMinBytes = 64ull << 20;
+void decide_sharding(hpf_ctx *c)
+{
+  c->shard_now = c->last_sharded = false;
+  if (c->nranks <= 1 || c->shard_mode == 0 || c->bias || c->logl || c->jacobi || c->mg_exact) return;
+  if (!g_nccl.ReduceScatter || !g_nccl.AllGather) return;
+  const uint64_t payload = (uint64_t)c->be.R * c->ld * sizeof(float);
+  if (c->shard_mode < 0 && payload < kShardMinBytes) return; // few items: the replicated update is cheaper than two more collectives
+  c->shard_now = c->last_sharded = true;
+  c->slice_rows = (c->be.R + (uint32_t)c->nranks - 1) / (uint32_t)c->nranks;
+}
+
+// end of a sharded window: the rest of beta's state, whole on every rank again
+int gather_beta_state(hpf_ctx *c)
+{
+  if (!c->shard_now) return 0;
+  CU(cudaEventRecord(c->ev_beta, c->stream));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_beta, 0));
+  const size_t rows = c->slice_rows;
+  if (g_nccl.GroupStart && g_nccl.GroupEnd) g_nccl.GroupStart();
+  int rc = comm_allgather(c, c->be.shape, rows * c->ld);
+  if (!rc) rc = comm_allgather(c, c->be.shift, rows);
+  if (!rc && c->hier) {
+    rc = comm_allgather(c, c->be.rate_row, rows);
+    if (!rc) rc = comm_allgather(c, c->be.pr_shape, rows);
+    if (!rc) rc = comm_allgather(c, c->be.pr_rate, rows);
+    if (!rc) rc = comm_allgather(c, c->be.pr_Ev, rows);
+  }
+  if (g_nccl.GroupStart && g_nccl.GroupEnd) {
+    const int grc = g_nccl.GroupEnd();
+    if (!rc && grc != ncclSuccess) rc = nccl_fail(c, grc, "ncclGroupEnd");
+  }
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  c->shard_now = false;
   return 0;
 }
 
@@ -991,7 +1077,20 @@ int one_iteration(hpf_ctx *c)
   STAGE_END(5);
   // beta: Gauss-Seidel uses the NEW sum_u E[theta] (hgaprec.cc:1380-1384), -novb the old one
   STAGE_BEGIN(6);
-  TRY(launch_update(c, c->be, c->jacobi ? c->colsum_theta_old : c->th.colsum, n_glob));
+  if (c->shard_now) {
+    const uint32_t r0 = std::min<uint64_t>((uint64_t)c->rank * c->slice_rows, c->be.R);
+    const uint32_t r1 = std::min<uint64_t>((uint64_t)(c->rank + 1) * c->slice_rows, c->be.R);
+    TRY(launch_update(c, c->be, c->th.colsum, n_glob, r0, r1 - r0));
+    // sum_i E[beta] over the slices, then the rows of A_beta the other ranks updated: all the next sweeps read
+    CU(cudaEventRecord(c->ev_beta, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_beta, 0));
+    TRY(comm_allreduce(c, c->be.colsum, c->Kp));
+    TRY(comm_allgather(c, c->be.A, (size_t)c->slice_rows * c->ld));
+    CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+  } else {
+    TRY(launch_update(c, c->be, c->jacobi ? c->colsum_theta_old : c->th.colsum, n_glob));
+  }
   STAGE_END(6);
   STAGE_END(7);
   c->iterations++;
@@ -1087,6 +1186,8 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
   if (const char *e = getenv("HPF_HEAD_VARIANT")) n->head_variant = atoi(e) & 7;
   if (const char *e = getenv("HPF_PACK")) n->pack_ok = atoi(e) != 0;
   if (const char *e = getenv("HPF_AR_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= (int)kMaxChunks) n->ar_chunks = v; }
+  if (const char *e = getenv("HPF_SHARD_BETA")) n->shard_mode = atoi(e);
+  if (const char *e = getenv("HPF_AR_DEFER")) n->ar_defer = atoi(e) != 0;
   if (const char *e = getenv("HPF_MG_EXACT")) n->mg_exact = atoi(e) != 0; // tests: fallback buffers inside the all-reduce from the start
   c = n;
   int rc = 0;
@@ -1106,7 +1207,8 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     if ((rc = alloc_side(c, c->be, cfg->n_items, false))) break;
     // item-side reduce blocks: [T_beta (m x ld) | Tb_beta (m, padded to 4) | colsum_theta (Kp) | flag (4)] and
     // [Tdirect_beta (m x ld) | Tbdirect_beta (m, padded to 4)]
-    const size_t mk = (size_t)cfg->n_items * c->ld, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
+    // (T_beta with kRowPad spare rows: the in-place reduce-scatter of the sharded beta update works on equal slices)
+    const size_t mk = ((size_t)cfg->n_items + kRowPad) * c->ld, mpad = c->bias ? (((size_t)cfg->n_items + 3) & ~(size_t)3) : 0;
     c->red_count = mk + mpad + c->Kp + 4;
     if ((rc = dalloc(c, &c->redblock, c->red_count))) break;
     c->be.T = c->redblock;
@@ -1114,10 +1216,11 @@ int hpf_create(const hpf_config *cfg, hpf_ctx **out)
     c->th.colsum = c->redblock + mk + mpad;
     c->red_tail = c->redblock + mk; c->red_tail_count = mpad + c->Kp + 4;
     c->red_flag = c->redblock + mk + mpad + c->Kp;
-    c->red2_count = mk + mpad;
+    const size_t mk2 = (size_t)cfg->n_items * c->ld;
+    c->red2_count = mk2 + mpad;
     if ((rc = dalloc(c, &c->redblock2, c->red2_count))) break;
     c->be.Tdirect = c->redblock2;
-    c->be.Tbdirect = c->bias ? c->redblock2 + mk : nullptr;
+    c->be.Tbdirect = c->bias ? c->redblock2 + mk2 : nullptr;
     if ((rc = dalloc(c, &c->mg_fired, 4))) break;
     if ((rc = dalloc(c, &c->be.colsum, c->Kp))) break;
     if ((rc = dalloc(c, &c->th.T, (size_t)cfg->n_users * c->ld))) break;
@@ -1162,6 +1265,7 @@ void hpf_destroy(hpf_ctx *c)
   for (auto &e : c->ev_chunk) if (e) cudaEventDestroy(e);
   if (c->ev_theta) cudaEventDestroy(c->ev_theta);
   if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+  if (c->ev_beta) cudaEventDestroy(c->ev_beta);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (auto &p : c->allocs) cudaFree(p.first);
   if (c->dev_arena.base) cudaFree(c->dev_arena.base);
@@ -1588,7 +1692,9 @@ int snapshot_state(hpf_ctx *c, bool restore)
 int run_window(hpf_ctx *c, uint32_t n_iters)
 {
   CU(cudaEventRecord(c->ev0, c->stream));
+  decide_sharding(c);
   for (uint32_t it = 0; it < n_iters; ++it) TRY(one_iteration(c));
+  TRY(gather_beta_state(c));
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -1625,6 +1731,8 @@ int hpf_iterate(hpf_ctx *c, uint32_t n_iters)
       // only.  Re-run the window from the snapshot with the fallback buffers inside the all-reduce, and stay there.
       c->mg_exact = true;
       TRY(snapshot_state(c, true));
+      // a sharded window consumed (and cleared) only each rank's own slice of the item side's fallback sums
+      CU(cudaMemsetAsync(c->redblock2, 0, c->red2_count * sizeof(float), c->stream));
       // rate, E[v] and E[log v] are never written inside a window (only derive_kernel and hpf_set_state write them): if
       // they were current when the window began they still are -- and after hpf_set_state they are NOT functions of
       // the shape (src/gpbase.hh:324-340), so the fallback of the first iteration must read them, not recompute them
@@ -1649,6 +1757,7 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
   TRY(check_ready(c));
   TRY(ensure_aux(c));
   float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  decide_sharding(c);
   for (uint32_t it = 0; it < n_iters; ++it) {
     c->profiling = true;
     int rc = one_iteration(c);
@@ -1662,6 +1771,8 @@ int hpf_iterate_profiled(hpf_ctx *c, uint32_t n_iters, hpf_iter_profile *out)
       acc[i] += ms;
     }
   }
+  TRY(gather_beta_state(c));
+  CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   const float inv = 1.f / (float)n_iters;
   out->sweep_user_ms = (acc[0] + acc[3]) * inv; out->sweep_item_ms = acc[1] * inv; out->combine_ms = acc[2] * inv;
@@ -2067,6 +2178,7 @@ int hpf_get_stats(const hpf_ctx *c, hpf_stats *out)
   out->item_chunks = c->be.wl.nchunks;
   out->mg_exact = c->mg_exact ? 1u : 0u;
   out->n_devices = 1;
+  out->beta_sharded = c->last_sharded ? 1u : 0u;
   return 0;
 }
 
@@ -2368,6 +2480,7 @@ int group_get_stats(const hpf_ctx *g, hpf_stats *out)
       out->user_l2_tiles = s.user_l2_tiles; out->item_l2_tiles = s.item_l2_tiles; out->item_chunks = s.item_chunks;
     }
     out->mg_exact |= s.mg_exact;
+    out->beta_sharded |= s.beta_sharded;
   }
   return 0;
 }

@@ -772,13 +772,15 @@ __global__ void __launch_bounds__(256) derive_kernel(const DeriveArgs a)
 // colsum[k] = sum over blocks of partial[b][k], accumulated in double in a fixed
 // order (one block per 32 columns, 32 row groups per block); also clears the side's
 // direct_flag for the next iteration.  Multi-GPU bookkeeping of the exact fallback
-// (one thread): flag_out[0] = 1.0 if *flag_in is set (the theta update publishes the
-// ITEM side's flag into the tail of the reduce block), sticky[0] += reduced[0] (the
+// (one thread): flag_out[0] = 1.0 if *flag_in (or *flag_in2, when given) is set (the
+// theta update publishes the ITEM side's flag -- with a sharded beta update also its
+// own -- into the tail of the reduce block), sticky[0] += reduced[0] (the
 // beta update accumulates the all-reduced flag; read by hpf_iterate at its end).
 constexpr int kFinalizeGroups = 32;
 __global__ void __launch_bounds__(32 * kFinalizeGroups) colsum_finalize_kernel(const float *partial, uint32_t nblocks, uint32_t Kp,
                                                              float *colsum, uint32_t *direct_flag, const uint32_t *flag_in,
-                                                             float *flag_out, const float *reduced, float *sticky)
+                                                             const uint32_t *flag_in2, float *flag_out, const float *reduced,
+                                                             float *sticky)
 {
   __shared__ double part[kFinalizeGroups][32];
   const uint32_t kx = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -795,7 +797,7 @@ __global__ void __launch_bounds__(32 * kFinalizeGroups) colsum_finalize_kernel(c
     colsum[k] = (float)t;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (flag_out != nullptr) flag_out[0] = *flag_in != 0u ? 1.f : 0.f;
+    if (flag_out != nullptr) flag_out[0] = (*flag_in != 0u || (flag_in2 != nullptr && *flag_in2 != 0u)) ? 1.f : 0.f;
     if (sticky != nullptr) sticky[0] += reduced[0];
     if (direct_flag != nullptr) *direct_flag = 0u;
   }

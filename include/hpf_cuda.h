@@ -127,6 +127,8 @@ typedef struct hpf_stats {
   float    last_topn_ms;     /* device time of the scoring + selection kernel(s) of
                                 the last hpf_topn                                   */
   uint32_t n_devices;        /* GPUs this ctx drives                                */
+  uint32_t beta_sharded;     /* 1: the last hpf_iterate ran the item side sharded over the ranks
+                                (reduce-scatter, each rank updates m/N items, all-gather) */
 } hpf_stats;
 
 /* Fill *cfg with the reference's defaults (all priors 0.3, device 0). */

@@ -138,9 +138,10 @@ def test_two_gpu_shards_match_single_gpu_and_oracle(flags):
     assert not bad, bad
 
 
-def _run_two_ranks(d, s, flags, iters, k, heldout=None):
+def _run_two_ranks(d, s, flags, iters, k, heldout=None, windows=None):
     """Two engines (GPU 0 and 1, one thread each) joined by NCCL over the nnz-balanced user partition.
-    Returns per rank (state dict, stats[, held-out ll sum of the rank's users])."""
+    Returns per rank (state dict, stats[, held-out ll sum of the rank's users]).  windows: the iterations as
+    several hpf_iterate calls (default: one)."""
     n, m = d["n"], d["m"]
     bounds = H.partition_users(d["row_ptr"], 2)
     rp = d["row_ptr"].astype(np.int64)
@@ -154,7 +155,8 @@ def _run_two_ranks(d, s, flags, iters, k, heldout=None):
                 e.comm_init(r, 2, uid)
                 e.set_ratings_csr(rp[lo:hi + 1] - rp[lo], d["col_idx"][rp[lo]:rp[hi]], None if d["y"] is None else d["y"][rp[lo]:rp[hi]])
                 util.push_state(e, s, users=np.arange(lo, hi))
-                e.iterate(iters)
+                for w in (windows or [iters]):
+                    e.iterate(w)
                 res = ({g: e.get_state(util._IDS[g]) for g in util.groups(s)}, e.stats())
                 if heldout is not None:
                     hu, hi_, hy, _ = heldout
@@ -282,3 +284,77 @@ def test_one_ctx_driving_two_gpus_is_bitwise_the_two_rank_run(flags):
     np.testing.assert_array_equal(scores, scores1)
     np.testing.assert_array_equal(ranks, ranks1)
     np.testing.assert_array_equal(rscores, rscores1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,dense", [(H.HIER, "0"), (0, "0"), (H.HIER, "1")])
+def test_two_gpu_sharded_beta_update_matches_the_replicated_one(monkeypatch, flags, dense):
+    """Many items (MSD): T_beta is reduce-scattered, each rank updates its slice of ceil(m / N) items, A_beta is
+    all-gathered every iteration and the rest of beta's state when the hpf_iterate window ends (HPF_SHARD_BETA; auto
+    from the payload).  Against the replicated update only the order of the sums behind sum_i E[beta] changes; m is odd
+    so the slices are unequal and the last one runs into the spare rows; two windows, so a window starts from gathered
+    state; every rank must hold the SAME beta afterwards (checked bitwise by _stitch)."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    monkeypatch.setenv("HPF_DENSE_HEAD", dense)
+    n, m, nnz, k, iters = 4000, 1001, 150000, 64, 3
+    d = synth.make_ratings(n, m, nnz, seed=43, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(44)
+    hu, hi_, hy = d["heldout"]
+    bounds = H.partition_users(d["row_ptr"], 2)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("HPF_SHARD_BETA", mode)
+        one = _stitch(_run_two_ranks(d, s, flags, 1, k), s, n, m, k, flags)
+        out = _run_two_ranks(d, s, flags, iters, k, heldout=(hu, hi_, hy, bounds), windows=[2, 1])
+        assert out[0][1]["beta_sharded"] == int(mode) and out[1][1]["beta_sharded"] == int(mode)
+        assert out[0][1]["mg_exact"] == 0 and (out[0][1]["head_nnz"] > 0) == (dense == "1")
+        runs[mode] = (one, _stitch(out, s, n, m, k, flags), out[0][2] + out[1][2])
+    bad = util.compare_states(runs["1"][0], runs["0"][0], rel=1e-5, elog_abs=1e-5)
+    assert not bad, bad
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters, nthreads=8)
+    bad = util.compare_states(runs["1"][1], want, rel=6e-5, elog_abs=6e-5)
+    assert not bad, bad
+    assert abs(runs["1"][2] - want.heldout(hu, hi_, hy)) / len(hu) <= 2e-4
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_beta_update_falls_back_to_the_exact_replicated_run(monkeypatch):
+    """Inside a sharded window the exact fallback would read rows of beta's shape another rank owns, so ANY fallback
+    raises the flag: the window re-runs from its snapshot unsharded, fallback buffers inside the all-reduce."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    monkeypatch.setenv("HPF_SHARD_BETA", "1")
+    flags = H.HIER
+    n, m, nnz, k, iters = 900, 401, 30000, 12, 2
+    d = synth.make_ratings(n, m, nnz, seed=5)
+    s = O.OracleState(n, m, k, flags).init(6)
+    s.p["theta"]["Elogv"][:, 1:] -= 200.0
+    s.p["beta"]["Elogv"][:, :-1] -= 200.0
+    want = s.copy().iterate(d["row_ptr"], d["col_idx"], d["y"], iters)
+    out = _run_two_ranks(d, s, flags, iters, k)
+    assert out[0][1]["mg_exact"] == 1 and out[1][1]["mg_exact"] == 1
+    assert out[0][1]["beta_sharded"] == 0 and out[0][1]["slow_path_nnz"] > 0
+    bad = util.compare_states(_stitch(out, s, n, m, k, flags), want, rel=6e-5, elog_abs=6e-5)
+    assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_one_ctx_driving_two_gpus_shards_the_beta_update_too(monkeypatch):
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    monkeypatch.setenv("HPF_SHARD_BETA", "1")
+    flags = H.HIER
+    n, m, nnz, k, iters = 4000, 1001, 150000, 64, 3
+    d = synth.make_ratings(n, m, nnz, seed=43)
+    s = O.OracleState(n, m, k, flags).init(44)
+    two = _stitch(_run_two_ranks(d, s, flags, iters, k), s, n, m, k, flags)
+    with H.Engine(n, m, k, flags=flags, devices=[0, 1]) as e:
+        e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+        util.push_state(e, s)
+        e.iterate(iters)
+        got = util.pull_state(e, s)
+        assert e.stats()["beta_sharded"] == 1
+    for g in util.groups(s):
+        for f in O.FIELDS:
+            np.testing.assert_array_equal(got.p[g][f], two.p[g][f], err_msg="%s.%s" % (g, f))
