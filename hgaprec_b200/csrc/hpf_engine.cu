@@ -242,7 +242,11 @@ struct hpf_ctx {
   // state (shape, xi/eta terms, shift) is gathered when the window of hpf_iterate ends, so every other entry point
   // sees whole arrays.  Inside a window the exact fallback would read stale rows of them: ANY fallback (user or item
   // side) raises the flag and the window re-runs unsharded in mg_exact mode.
-  int shard_mode = -1;            // HPF_SHARD_BETA: -1 auto (payload >= kShardMinBytes), 0 off, 1 on
+  // Measured on 8 x B200 at MSD scale (profiles/r02t_bench_n8_msd_{replicated,sharded}.json): 2.26 ms against 2.33 ms
+  // replicated -- the all-gather of A_beta (0.55 ms) cannot hide under anything, while the replicated form's all-reduce
+  // hides under the user pass and the theta update; with the faster update kernel that followed the replicated form
+  // is ahead, and at 2 GPUs it always was (6.40 vs 6.51 ms).  So: opt-in.
+  int shard_mode = 0;             // HPF_SHARD_BETA: 0 off (default), 1 on, -1 on when the payload >= kShardMinBytes
   bool shard_now = false;         // this window runs sharded
   bool last_sharded = false;      // ... the last one did (hpf_stats)
   uint32_t slice_rows = 0;        // ceil(m / N)
@@ -321,7 +325,7 @@ uint32_t row_grid(const hpf_ctx *c, uint32_t R)
 template <int V> int update_occupancy()
 {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, update_kernel<V>, kUpdateWarps * 32, 0) != cudaSuccess || occ < 1) occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, update_kernel<V, false>, kUpdateWarps * 32, 0) != cudaSuccess || occ < 1) occ = 1;
   return occ;
 }
 uint32_t update_grid_for(const hpf_ctx *c, uint32_t R)
@@ -478,7 +482,8 @@ int launch_combine(hpf_ctx *c, Side &s, int chunk = -1)
 template <int V> int launch_update_v(hpf_ctx *c, const UpdateArgs &a, uint32_t grid)
 {
   const size_t sm = (size_t)kUpdateWarps * c->Kp * sizeof(float);
-  update_kernel<V><<<grid, kUpdateWarps * 32, sm, c->stream>>>(a);
+  if (a.K == a.Kp) update_kernel<V, true><<<grid, kUpdateWarps * 32, sm, c->stream>>>(a);
+  else update_kernel<V, false><<<grid, kUpdateWarps * 32, sm, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -991,7 +996,7 @@ int comm_allgather(hpf_ctx *c, float *base, size_t count)
   return rc == ncclSuccess ? 0 : nccl_fail(c, rc, "ncclAllGather");
 }
 
-// sharded beta update: does this window qualify?  Every input is the same on all ranks.
+// sharded beta update (opt-in): does this window qualify?  Every input is the same on all ranks.
 constexpr uint64_t kShardMinBytes = 64ull << 20;
 void decide_sharding(hpf_ctx *c)
 {

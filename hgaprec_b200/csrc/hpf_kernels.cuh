@@ -91,12 +91,37 @@ __device__ __forceinline__ float floor30(float v) { return v > 0.f ? v : 1e-30f;
 
 // digamma for x > 0 in fp32: upward recurrence to x >= 6, then the Stirling
 // series.  Replaces gsl_sf_psi at gpbase.hh:260,593,923.
-__device__ __forceinline__ float digammaf(float x)
+// The special-function unit's approximations, without the denormal rescaling nvcc wraps around them (every argument
+// here is a normal number: shapes and rates are floored at 1e-30): rcp 1 ulp, lg2 absolute error 2^-22, ex2 2 ulp.
+__device__ __forceinline__ float rcp_fast(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float log_fast(float x) // absolute error <= 2e-7 + 1 ulp: what E[log v] = psi(shape) - log(rate) can carry
+{
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.693147182f;
+}
+__device__ __forceinline__ float exp_fast(float x) // x <= 0; relative error 2 ulp + |x| * 2^-24
+{
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.44269502f));
+  return r;
+}
+
+// CONVERGED: all 32 lanes of the warp are here, so the recurrence is skipped by a warp vote when no lane needs it
+// (rows of large shapes) and costs no divergence when some do; same arithmetic, same bits either way.
+template <bool CONVERGED = false> __device__ __forceinline__ float digammaf(float x)
 {
   // psi(x) = psi(x + 6) - sum_{i<6} 1/(x + i); the sum is formed as ONE quotient p/q
-  // (q = prod (x+i), p = sum of the products leaving one factor out): one division instead of six
+  // (q = prod (x+i), p = sum of the products leaving one factor out): one division instead of six.
+  // No per-lane branch: lanes of a warp fall on both sides of 6, and the four values a lane works on overlap.
+  const bool small = x < 6.f;
   float r = 0.f;
-  if (x < 6.f) {
+  if (!CONVERGED || __any_sync(0xffffffffu, small)) {
     float q = x, p = 1.f;
 #pragma unroll
     for (int i = 1; i < 6; ++i) {
@@ -104,13 +129,20 @@ __device__ __forceinline__ float digammaf(float x)
       p = fmaf(p, t, q);
       q *= t;
     }
-    r = -__fdividef(p, q);
-    x += 6.f;
+    r = small ? -p * rcp_fast(q) : 0.f; // (x >= 6: p / q may be inf / inf -- never selected)
   }
-  const float inv = __fdividef(1.f, x);
+  x = small ? x + 6.f : x;
+  const float inv = rcp_fast(x);
   const float f = inv * inv;
   const float t = f * (-1.f / 12.f + f * (1.f / 120.f + f * (-1.f / 252.f + f * (1.f / 240.f))));
-  return r + __logf(x) - 0.5f * inv + t;
+  return r + log_fast(x) - 0.5f * inv + t;
+}
+
+// E[log v] = psi(shape) - log(rate) as update_kernel, derive_kernel and the exact fallback's load_elog4 all form it
+// (the same operations, so the three agree bit for bit)
+template <bool CONVERGED = false> __device__ __forceinline__ float elog_of(float shape_floored, float rate_floored)
+{
+  return digammaf<CONVERGED>(shape_floored) - log_fast(rate_floored);
 }
 
 // ---------------------------------------------------------------------------
@@ -143,7 +175,7 @@ __device__ __forceinline__ float4 load_elog4(const ElogSrc &e, uint32_t row, uin
   float *o = reinterpret_cast<float *>(&out);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    o[j] = q * 4 + j < K ? digammaf(floor30(s[j])) - logf(floor30(e.hier ? rr + c[j] : c[j])) : -CUDART_INF_F;
+    o[j] = q * 4 + j < K ? elog_of(floor30(s[j]), floor30(e.hier ? rr + c[j] : c[j])) : -CUDART_INF_F;
   return out;
 }
 
@@ -572,7 +604,9 @@ __device__ __forceinline__ float f4get(const float4 &v, int j) { return reinterp
 // resident blocks the register budget is set for: V float4 per lane of row operands, twice (two rows in flight)
 constexpr int update_min_blocks(int V) { return V <= 2 ? 3 : (V <= 4 ? 2 : 1); }
 
-template <int V>
+// FULL: K is a multiple of 4, so every float4 a lane works on holds four live factors and the per-value bounds
+// checks (one reconvergence region each, which kept the four chains from overlapping) disappear
+template <int V, bool FULL>
 __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) update_kernel(const UpdateArgs a)
 {
   extern __shared__ float cs[]; // [kUpdateWarps][Kp] column partial sums of Ev
@@ -602,58 +636,56 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
   float4 av[V], tv[V];
   if (r < a.R) {
 #pragma unroll
-    for (int v = 0; v < V; ++v)
+    for (int v = 0; v < V; ++v) {
+      av[v] = tv[v] = make_float4(0.f, 0.f, 0.f, 0.f); // lanes past the row's end work on zeros (all 32 stay converged)
       if (act[v]) {
         av[v] = a.A[(size_t)r * a.ld4 + lane + 32 * v];
         tv[v] = __ldg(a.T + (size_t)r * a.ld4 + lane + 32 * v);
       }
+    }
   }
   for (; r < a.R; r += warps_total) {
     const size_t base = (size_t)r * a.ld4;
     // the next row's operands are requested before this row's arithmetic (two rows in flight per warp)
     const uint32_t rn = r + warps_total;
     float4 an[V], tn[V];
-    if (rn < a.R) {
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (act[v]) {
-          an[v] = a.A[(size_t)rn * a.ld4 + lane + 32 * v];
-          tn[v] = __ldg(a.T + (size_t)rn * a.ld4 + lane + 32 * v);
-        }
+    for (int v = 0; v < V; ++v) {
+      an[v] = tn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rn < a.R && act[v]) {
+        an[v] = a.A[(size_t)rn * a.ld4 + lane + 32 * v];
+        tn[v] = __ldg(a.T + (size_t)rn * a.ld4 + lane + 32 * v);
+      }
     }
     const float rprior = a.hier ? a.pr_Ev[r] : a.prior_rate;
     float mx = -CUDART_INF_F, rowsum = 0.f;
     float4 el[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      if (!act[v]) continue;
       const uint32_t q = lane + 32 * v;
       float4 sh;
       float4 td = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (use_direct) {
+      if (use_direct && act[v]) {
         td = a.Tdirect[base + q];
         a.Tdirect[base + q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (q * 4 + j < a.K) {
-          float s = a.prior_shape + f4get(av[v], j) * f4get(tv[v], j);
-          if (use_direct) s += f4get(td, j);
-          const float rt = rprior + f4get(cterm[v], j);
-          const float sa = floor30(s), rb = floor30(rt);
-          const float ev = __fdividef(sa, rb); // 2 ulp: feeds the row / column sums only (derive_kernel repeats it)
-          const float e = digammaf(sa) - logf(rb);
-          f4at(sh, j) = s;
-          f4at(el[v], j) = e;
-          mx = fmaxf(mx, e);
-          rowsum += ev;
-          f4at(csum[v], j) += ev;
-        } else {
-          f4at(sh, j) = 0.f;
-          f4at(el[v], j) = -CUDART_INF_F;
-        }
+      for (int j = 0; j < 4; ++j) { // every lane, live value or not: the warp stays converged for digammaf's vote
+        const bool live = act[v] && (FULL || q * 4 + j < a.K);
+        float s = a.prior_shape + f4get(av[v], j) * f4get(tv[v], j);
+        if (use_direct) s += f4get(td, j);
+        const float rt = rprior + f4get(cterm[v], j);
+        const float sa = floor30(s), rb = floor30(rt);
+        const float ev = live ? sa * rcp_fast(rb) : 0.f; // 1 ulp: feeds the row / column sums only (derive_kernel repeats it)
+        const float e0 = elog_of<true>(sa, rb); // outside the select: the vote inside needs every lane
+        const float e = live ? e0 : -CUDART_INF_F;
+        f4at(sh, j) = live ? s : 0.f;
+        f4at(el[v], j) = e;
+        mx = fmaxf(mx, e);
+        rowsum += ev;
+        f4at(csum[v], j) += ev;
       }
-      a.shape[base + q] = sh;
+      if (act[v]) a.shape[base + q] = sh;
     }
     mx = warp_max(mx);
     rowsum = warp_sum(rowsum);
@@ -663,7 +695,7 @@ __global__ void __launch_bounds__(kUpdateWarps * 32, update_min_blocks(V)) updat
       const uint32_t q = lane + 32 * v;
       float4 an4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) f4at(an4, j) = q * 4 + j < a.K ? expf(f4get(el[v], j) - mx) : 0.f;
+      for (int j = 0; j < 4; ++j) f4at(an4, j) = (FULL || q * 4 + j < a.K) ? exp_fast(f4get(el[v], j) - mx) : 0.f;
       a.A[base + q] = an4;
       if (a.split_hi != nullptr) { // x = hi + lo in bf16 (representation error 2^-18)
         __nv_bfloat16 h[4], l[4];
@@ -755,8 +787,8 @@ __global__ void __launch_bounds__(256) derive_kernel(const DeriveArgs a)
         const float t = a.hier ? rr + f4get(ct, j) : f4get(ct, j);
         const float sa = floor30(f4get(sh, j)), rb = floor30(t);
         f4at(rt, j) = t;
-        f4at(ev, j) = __fdividef(sa, rb); // the operation update_kernel used for its sums
-        f4at(el, j) = digammaf(sa) - logf(rb);
+        f4at(ev, j) = sa * rcp_fast(rb); // the operation update_kernel used for its sums
+        f4at(el, j) = elog_of(sa, rb);
       } else {
         f4at(rt, j) = 1.f;
         f4at(ev, j) = 0.f;
