@@ -445,7 +445,7 @@ void HGAPRec::gen_ranking_for_users(bool load)
   }
   sampled_users_.clear();
   if (!ratings_.read_test_users(opt_.dir + "/test_users.tsv", &sampled_users_)) {
-    fprintf(stderr, "cannot open %s/test_users.tsv\n", opt_.dir.c_str());
+    fprintf(stderr, "cannot read %s/test_users.tsv (missing or malformed)\n", opt_.dir.c_str());
     return;
   }
   compute_precision(true);

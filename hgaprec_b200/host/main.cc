@@ -110,7 +110,7 @@ int main(int argc, char **argv)
   fflush(stdout);
   std::string err;
   if (!ratings.read_train(o.dir, &err, o.csr_cache)) {
-    fprintf(stderr, "error: %s", err.c_str());
+    fprintf(stderr, "error: %s\n", err.c_str());
     exit(-1);
   }
   if (o.csr_cache) fprintf(stdout, "+ csr cache: %s\n", ratings.cache_note().c_str());

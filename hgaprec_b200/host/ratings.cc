@@ -152,7 +152,11 @@ bool TripleReader::number(uint32_t *out)
     neg = ch == '-';
     ch = get();
   }
-  if (ch < '0' || ch > '9') return false;
+  if (ch < '0' || ch > '9') { // not a number: the caller must not mistake this for the end of the input
+    bad_ = true;
+    bad_at_ = base_ + pos_ - (ch < 0 ? 0 : 1);
+    return false;
+  }
   uint32_t v = 0;
   while (ch >= '0' && ch <= '9') {
     v = v * 10u + (uint32_t)(ch - '0');
@@ -210,6 +214,10 @@ bool Ratings::read_train(const std::string &dir, std::string *err, bool use_cach
     vals_[u].push_back(binary_ ? (uint8_t)1 : (uint8_t)rating);
   }
   fclose(f);
+  if (rd.bad()) { // never train on (or cache) a silently truncated matrix
+    *err = rd.complaint(path);
+    return false;
+  }
   finalize();
   if (use_cache) save_cache(path, cache);
   return true;
@@ -255,6 +263,10 @@ bool Ratings::read_heldout(const std::string &path, HeldoutMap *out, std::string
     (*out)[Pair(ut->second, it->second)] = binary_ ? (uint8_t)1 : (uint8_t)rating;
   }
   fclose(f);
+  if (rd.bad()) {
+    *err = rd.complaint(path);
+    return false;
+  }
   return true;
 }
 
@@ -269,7 +281,7 @@ bool Ratings::read_test_users(const std::string &path, std::map<uint32_t, bool> 
     if (ut != user2seq_.end()) (*out)[ut->second] = true;
   }
   fclose(f);
-  return true;
+  return !rd.bad();
 }
 
 void Ratings::to_csr(std::vector<uint64_t> *row_ptr, std::vector<uint32_t> *col_idx, std::vector<uint8_t> *y) const

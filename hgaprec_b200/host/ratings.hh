@@ -40,14 +40,30 @@ typedef std::map<Pair, uint8_t> HeldoutMap;          // CountMap, iterated in (u
 // whitespace-separated unsigned integers from a file, three per record ("%u\t%u\t%u\n")
 class TripleReader {
 public:
-  explicit TripleReader(FILE *f) : f_(f), buf_(1 << 22), pos_(0), end_(0) {}
-  bool next(uint32_t *a, uint32_t *b, uint32_t *c) { return number(a) && number(b) && number(c); }
+  explicit TripleReader(FILE *f) : f_(f), buf_(1 << 22), pos_(0), end_(0), base_(0), bad_(false), bad_at_(0) {}
+  // one line of three numbers; false at the end of the input AND at a malformed token (bad() tells which): a line
+  // cut short by the end of the file counts as malformed
+  bool next(uint32_t *a, uint32_t *b, uint32_t *c)
+  {
+    if (!number(a)) return false;
+    if (number(b) && number(c)) return true;
+    if (!bad_) { bad_ = true; bad_at_ = base_ + pos_; }
+    return false;
+  }
   bool number(uint32_t *out);
+  // a token that is not an unsigned decimal stopped the reader (a header line, a float, a stray character)
+  bool bad() const { return bad_; }
+  uint64_t bad_offset() const { return bad_at_; }
+  std::string complaint(const std::string &path) const
+  {
+    return "malformed input in " + path + " at byte " + std::to_string(bad_at_) + ": expected unsigned decimal numbers";
+  }
 
 private:
   int get()
   {
     if (pos_ == end_) {
+      base_ += end_;
       end_ = fread(buf_.data(), 1, buf_.size(), f_);
       pos_ = 0;
       if (end_ == 0) return -1;
@@ -57,6 +73,9 @@ private:
   FILE *f_;
   std::vector<char> buf_;
   size_t pos_, end_;
+  uint64_t base_; // file offset of buf_[0]
+  bool bad_;
+  uint64_t bad_at_;
 };
 
 class Ratings {

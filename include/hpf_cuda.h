@@ -188,7 +188,11 @@ HPF_API int hpf_heldout_loglik(hpf_ctx *ctx, const uint32_t *u, const uint32_t *
  * least one hpf_iterate must have run since THETARATE / BETARATE were set (the reference only
  * calls logl() inside the loop).  Multi-GPU: the value is this rank's part -- its users'
  * nonzeros and user-side sets, plus the (replicated) item-side sets on rank 0 only -- so the sum
- * over the ranks is the ELBO of the whole problem. */
+ * over the ranks is the ELBO of the whole problem.
+ * Known deviation: a rating that wrapped to 0 in the reference's uint8 (256, 512, ...) is a 1 in
+ * the CSR (see hpf_set_ratings_csr).  The reference's logl() multiplies such an entry's entropy
+ * terms by the raw 0, so it contributes only -E[theta].E[beta] there, and the full y = 1 term
+ * here; the sweeps, the held-out likelihood and the rankings are unaffected. */
 HPF_API int hpf_elbo(hpf_ctx *ctx, double *elbo_out);
 
 /* compute_precision's scoring pass (src/hgaprec.cc:1703-1763, 1969-1991): for

@@ -81,6 +81,27 @@ def test_reader_edge_cases(hostcheck, tmp_path):
     np.testing.assert_array_equal(d["test.y"], [1])
 
 
+@pytest.mark.parametrize("bad,where", [("user\titem\trating\n1\t2\t3\n", "train"),       # header line
+                                       ("1\t2\t3\n4\t5\t2.5\n6\t7\t1\n", "train"),          # float rating
+                                       ("1\t2\t3\n4\t5\n", "train"),                          # line cut short by the end
+                                       ("1\t2\t3\n4\tx\t1\n", "validation")])
+def test_reader_stops_on_malformed_input_instead_of_truncating(hostcheck, tmp_path, bad, where):
+    """A token that is not an unsigned decimal is not the end of the input: the reader names the file and the byte and
+    the run stops -- it must not train on (or write a -csr-cache of) the lines before it."""
+    data = str(tmp_path / "d")
+    os.makedirs(data)
+    good = "1\t2\t3\n4\t5\t1\n"
+    for name in ("train", "validation", "test"):
+        open(os.path.join(data, name + ".tsv"), "w").write(bad if name == where else good)
+    p = subprocess.run([hostcheck, "-dir", data, "-n", "4", "-m", "8", "-k", "3", "-hier", "-csr-cache", "-out", str(tmp_path / "o.bin")],
+                       capture_output=True, text=True)
+    assert p.returncode != 0
+    assert "malformed input" in p.stderr and where + ".tsv" in p.stderr and "byte" in p.stderr, p.stderr
+    if where == "train":
+        assert not os.path.exists(os.path.join(data, "train.tsv.hpfcsr"))
+    assert not os.path.exists(str(tmp_path / "o.bin"))
+
+
 def _run_check(hostcheck, data, out, *extra):
     p = subprocess.run([hostcheck, "-dir", data, "-out", out] + list(extra), check=True, capture_output=True, text=True)
     return p.stdout
