@@ -358,3 +358,27 @@ def test_one_ctx_driving_two_gpus_shards_the_beta_update_too(monkeypatch):
     for g in util.groups(s):
         for f in O.FIELDS:
             np.testing.assert_array_equal(got.p[g][f], two.p[g][f], err_msg="%s.%s" % (g, f))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [H.HIER, H.BIAS])
+def test_two_gpus_against_one_after_20_iterations(flags):
+    """SURVEY.md 8e, second half of the gate: after 20 iterations the G-GPU fit and the 1-GPU fit differ by fp32
+    summation order only -- |delta mean held-out ll| <= 1e-5 (and the states stay within the 20-iteration band)."""
+    if not _two_gpus():
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    n, m, nnz, k, iters = 5000, 1200, 200000, 100, 20
+    d = synth.make_ratings(n, m, nnz, seed=23, heldout=0.05)
+    s = O.OracleState(n, m, k, flags).init(24)
+    hu, hi_, hy = d["heldout"]
+    res = {}
+    for name, kw in (("one", dict(device=0)), ("two", dict(devices=[0, 1]))):
+        with H.Engine(n, m, k, flags=flags, **kw) as e:
+            e.set_ratings_csr(d["row_ptr"], d["col_idx"], d["y"])
+            util.push_state(e, s)
+            e.iterate(iters)
+            res[name] = (util.pull_state(e, s), e.heldout_loglik(hu, hi_, hy) / len(hu), e.stats())
+    assert res["two"][2]["n_devices"] == 2 and res["two"][2]["slow_path_nnz"] == 0
+    assert abs(res["one"][1] - res["two"][1]) <= 1e-5, (res["one"][1], res["two"][1])
+    bad = util.compare_states(res["two"][0], res["one"][0], rel=2e-3, elog_abs=2e-3)
+    assert not bad, bad
