@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round (one GPU): what round 1 built after its GPU budget ran out, measured.
-#   gpurun --timeout 1500 -- 'bash tools/r02_first_call.sh'
+#   gpurun --timeout 1500 -- 'bash tools/calls/r02_first_call.sh'
 # Two-GPU follow-up (overlap of the all-reduce, 2-GPU tests):
 #   gpurun --gpus 2 --timeout 900 -- 'python -m pytest tests/test_multigpu.py tests/test_zz_elbo_gpu.py -m gpu -q > gpurun_out/pytest_2gpu.log 2>&1;
 #     for o in 0 1; do HPF_AR_OVERLAP=$o python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
