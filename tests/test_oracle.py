@@ -12,6 +12,7 @@ import pytest
 
 import util
 from oracle import hpf_oracle as O
+from hgaprec_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -241,3 +242,35 @@ def test_oracle_and_host_reader_pinned_on_movielens_k100_t21(tmp_path):
     row = open(os.path.join(util.MOVIELENS, "cli", "validation.txt")).read().splitlines()[-1].split("\t")
     assert int(row[0]) == 20 and int(row[3]) == 8001
     assert abs(float(row[2]) - float(z["T21/validation.ll_sum"][0]) / 8001) <= 1e-8
+
+
+def test_numpy_ranking_checkers_agree_with_the_oracle():
+    """tests/util.py's check_topn_rows / check_rank_rows (used by the 60K-user GPU ranking test, where the oracle's
+    full sort per user would take minutes) accept the oracle's own lists and reject a damaged one."""
+    n, m, k = 300, 500, 20
+    d = synth.make_ratings(n, m, 9000, seed=3)
+    s = O.OracleState(n, m, k, 1).init(4)   # 1 = HPF_HIER
+    s.iterate(d["row_ptr"], d["col_idx"], d["y"], 2)
+    users = np.array([0, 7, 299, 150, 33], np.uint32)
+    rp = d["row_ptr"].astype(np.int64)
+    ep = np.zeros(len(users) + 1, np.uint64)
+    ep[1:] = np.cumsum([rp[u + 1] - rp[u] for u in users])
+    ei = np.concatenate([d["col_idx"][rp[u]:rp[u + 1]] for u in users]).astype(np.uint32)
+    Et, Eb = s.p["theta"]["Ev"], s.p["beta"]["Ev"]
+    items, scores = s.topn(users, ep, ei, 50)
+    assert util.check_topn_rows(Et, Eb, users, ep, ei, items, scores, range(len(users))) == len(users)
+    full, _ = s.topn(users, ep, ei, m)
+    qp = np.arange(0, 4 * len(users) + 1, 4, dtype=np.uint64)
+    qi = np.tile(np.array([3, 499, 250, 0], np.uint32), len(users))
+    qi[0] = ei[0]                                              # an excluded item: ranks among the zeros
+    ranks = np.array([int(np.where(full[a] == qi[q])[0][0]) for a in range(len(users)) for q in range(4 * a, 4 * a + 4)])
+    assert util.check_rank_rows(Et, Eb, users, ep, ei, qp, qi, ranks, range(len(users))) == len(qi)
+    bad = scores.copy(); bad[1, 10] *= 1.01
+    with pytest.raises(AssertionError):
+        util.check_topn_rows(Et, Eb, users, ep, ei, items, bad, range(len(users)))
+    swapped = items.copy(); swapped[2, [0, 40]] = swapped[2, [40, 0]]
+    with pytest.raises(AssertionError):
+        util.check_topn_rows(Et, Eb, users, ep, ei, swapped, scores, range(len(users)))
+    off = ranks.copy(); off[5] += 3
+    with pytest.raises(AssertionError):
+        util.check_rank_rows(Et, Eb, users, ep, ei, qp, qi, off, range(len(users)))

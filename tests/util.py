@@ -156,3 +156,45 @@ def fingerprint(state, rng_seed=20131103, sample=4096):
             else:
                 out[key] = a.copy()
     return out
+
+
+# ---------------------------------------------------------------- ranking checks against plain numpy (any size)
+def _scores_fp64(Et, Eb, u, excl):
+    sc = np.asarray(Et[u], np.float64) @ np.asarray(Eb, np.float64).T
+    sc[excl] = 0.0          # excluded items stay candidates with score 0 (src/hgaprec.cc:1736-1741)
+    return sc
+
+
+def check_topn_rows(Et, Eb, users, excl_ptr, excl_idx, items, scores, rows, rel=1e-4):
+    """For the listed rows of a topn result: the scores are the best topn of E[theta_u].E[beta]^T (excluded -> 0) within
+    `rel`, every returned item really has the score returned with it, and no item appears twice.  Returns the number
+    of rows checked; raises AssertionError with the row otherwise."""
+    topn = items.shape[1]
+    for a in rows:
+        u = int(users[a])
+        sc = _scores_fp64(Et, Eb, u, excl_idx[int(excl_ptr[a]):int(excl_ptr[a + 1])])
+        want = np.sort(sc)[::-1][:topn]
+        got = np.asarray(scores[a], np.float64)
+        assert np.all(np.abs(got - want) <= rel * np.maximum(want, 1e-30)), ("scores", a, u)
+        assert np.all(np.abs(sc[items[a]] - got) <= rel * np.maximum(got, 1e-30)), ("item/score pairing", a, u)
+        assert len(set(items[a].tolist())) == topn, ("duplicate item", a, u)
+        assert np.all(np.diff(got) <= 0), ("order", a, u)
+    return len(rows)
+
+
+def check_rank_rows(Et, Eb, users, excl_ptr, excl_idx, query_ptr, query_idx, ranks, rows, rel=4e-6):
+    """For the listed rows of an item_ranks result: rank = number of items ahead in the descending list (ties by
+    ascending item), allowed to move within the run of scores closer than `rel` to the query's."""
+    m = Eb.shape[0]
+    idx = np.arange(m)
+    n = 0
+    for a in rows:
+        u = int(users[a])
+        sc = _scores_fp64(Et, Eb, u, excl_idx[int(excl_ptr[a]):int(excl_ptr[a + 1])])
+        for q in range(int(query_ptr[a]), int(query_ptr[a + 1])):
+            it = int(query_idx[q])
+            want = int(np.sum(sc > sc[it]) + np.sum((sc == sc[it]) & (idx < it)))
+            near = int(np.sum(np.abs(sc - sc[it]) <= rel * max(sc[it], 1e-30))) if sc[it] > 0 else 1
+            assert abs(int(ranks[q]) - want) < near + 1, ("rank", a, u, it, int(ranks[q]), want, near)
+            n += 1
+    return n
