@@ -493,6 +493,7 @@ def main():
                     "dense_head_nnz": int(ss["stats"]["head_nnz"]), "per_kernel_ms": ss["prof"]}
         except Exception as ex:  # a secondary leg must not take the headline down with it
             extras["extras_error"] = repr(ex)
+            print("bench.py: a secondary leg FAILED (%r); see extras_error in the line" % (ex,), file=sys.stderr, flush=True)
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -509,6 +510,8 @@ def main():
                                "core busy; the reference itself has no threads)"}}
         except Exception as ex:  # the baseline must not take the GPU number down with it
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)}
+            print("bench.py: the CPU baseline leg FAILED (%r); the line is printed with cpu_baseline.kind = "
+                  "'unavailable'" % (ex,), file=sys.stderr, flush=True)
 
     if rank == 0:
         shard = " (users sharded over %d GPUs, items replicated)" % world if world > 1 else ""
