@@ -162,6 +162,11 @@ bool TripleReader::number(uint32_t *out)
     v = v * 10u + (uint32_t)(ch - '0');
     ch = get();
   }
+  if (!(ch < 0 || ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r')) { // "2.5", "12abc": not a number either
+    bad_ = true;
+    bad_at_ = base_ + pos_ - 1;
+    return false;
+  }
   *out = neg ? 0u - v : v;
   return true;
 }

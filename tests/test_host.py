@@ -83,6 +83,8 @@ def test_reader_edge_cases(hostcheck, tmp_path):
 
 @pytest.mark.parametrize("bad,where", [("user\titem\trating\n1\t2\t3\n", "train"),       # header line
                                        ("1\t2\t3\n4\t5\t2.5\n6\t7\t1\n", "train"),          # float rating
+                                       ("1\t2\t3.5\n4\t5\t2.5\n6\t7\t1.5\n", "train"),      # ... on every line: 12 tokens, 4 "triples"
+                                       ("1\t2\t3\n4x\t5\t2\n", "train"),                      # digits followed by a letter
                                        ("1\t2\t3\n4\t5\n", "train"),                          # line cut short by the end
                                        ("1\t2\t3\n4\tx\t1\n", "validation")])
 def test_reader_stops_on_malformed_input_instead_of_truncating(hostcheck, tmp_path, bad, where):
